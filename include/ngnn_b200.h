@@ -1,0 +1,188 @@
+/*
+ * ngnn_b200.h — C ABI of libngnn_b200.so (sm_100a only).
+ *
+ * This is the drop-in boundary for the GraphSAGE mini-batch hot path of
+ * hhilsber/noise-GNN.  The reference has no native code: its hot path is two
+ * third-party Python entry points,
+ *     torch_geometric.nn.SAGEConv            (reference src/models/layers/sage.py:4,16-19,34,52)
+ *     torch_geometric.loader.NeighborLoader  (reference src/pipeline.py:6,75-92,152)
+ * and each function below names the piece of those two it replaces.
+ *
+ * Conventions (all functions):
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the
+ *     parameter is documented "(host)".  Nothing is retained after return.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), asynchronously;
+ *     no internal synchronisation and no hidden allocation, so every call is
+ *     CUDA-graph capturable.  Scratch memory comes from the caller through
+ *     (ws, ws_bytes); the matching *_workspace_bytes() gives the size.
+ *   - return value: NGNN_OK (0) or a negative NGNN_E_* code; the message of the
+ *     last failure on the calling thread is read with ngnn_last_error().
+ *   - index dtype is int32 at this ABI (the COO import/export take PyG's int64).
+ *   - matrices are row-major fp32 with an explicit leading dimension (in elements).
+ */
+#ifndef NGNN_B200_H
+#define NGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGNN_OK             0
+#define NGNN_E_INVALID     -1   /* bad shape / null pointer / bad flag            */
+#define NGNN_E_ALIGN       -2   /* pointer or leading dimension not aligned       */
+#define NGNN_E_CUDA        -3   /* a CUDA runtime call failed                     */
+#define NGNN_E_WORKSPACE   -4   /* workspace too small                            */
+#define NGNN_E_UNSUPPORTED -5   /* valid request outside what the kernels cover   */
+
+#define NGNN_ACT_NONE 0
+#define NGNN_ACT_RELU 1
+
+typedef void* ngnn_stream_t;     /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------- */
+int32_t ngnn_version(void);                              /* 10000*major+100*minor+patch */
+int32_t ngnn_last_error(char* buf, size_t cap);          /* copies a NUL-terminated message */
+/* 1 if the current device is compute capability 10.x (the only one the cubin runs on). */
+int32_t ngnn_device_supported(void);
+/* Total number of device kernels this library has launched in the process (monotonic); bench.py
+ * differences it around the timed region to report gpu_launches.                               */
+uint64_t ngnn_launch_count(void);
+
+/* ---- block structure (replaces PyG's COO->CSC conversion) ---- */
+/* Stable sort of a COO edge list by destination:
+ *   perm = argsort_stable(dst); col = src[perm]; rowptr[i] = #edges with dst < i.
+ * Bit-exact target: oracle/structure.py::coo_to_csr.                                  */
+size_t  ngnn_coo_to_csr_workspace_bytes(int64_t e, int64_t n_rows);
+int32_t ngnn_coo_to_csr(const int64_t* src, const int64_t* dst, int64_t e, int64_t n_rows,
+                        int32_t* rowptr /*[n_rows+1]*/, int32_t* col /*[e]*/, int32_t* perm /*[e]*/,
+                        void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* Transpose of a CSR block (CSC by source) for the atomic-free backward:
+ *   perm_t = argsort_stable(col); row_t = dst_of_edge[perm_t]; colptr_t over n_cols.
+ * Only the first e_limit edges (a hop prefix) take part.                               */
+size_t  ngnn_csr_transpose_workspace_bytes(int64_t e, int64_t n_cols);
+int32_t ngnn_csr_transpose(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t e_limit,
+                           int64_t n_cols, int32_t* colptr_t /*[n_cols+1]*/, int32_t* row_t /*[e_limit]*/,
+                           int32_t* perm_t /*[e_limit]*/, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* CSR -> PyG edge_index int64 [2,e] (row 0 = source, row 1 = destination). */
+int32_t ngnn_csr_to_coo(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t e,
+                        int64_t* edge_index /*[2*e]*/, ngnn_stream_t stream);
+
+/* out[i,:] = table[idx[i],:]  (NeighborLoader's x[n_id] slice). */
+int32_t ngnn_gather_rows(const float* table, int64_t ld_table, const int32_t* idx, int64_t n, int64_t F,
+                         float* out, int64_t ld_out, ngnn_stream_t stream);
+
+/* ---- K-AGG: CSR segment mean (SAGEConv's MeanAggregation) ----
+ *   mean[i,:] = (1/max(deg_i,1)) * sum_{p in [rowptr[i],rowptr[i+1])} x[col[p],:]   for i < n_dst
+ * Optional fused root gather: if root_idx != NULL, root[i,:] = x[root_idx[i],:].
+ * x is any row-major table (a block's x[n,F] or the resident feature table with
+ * global ids in col).  No atomics: one warp (or sub-warp) owns one destination row. */
+int32_t ngnn_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const float* x, int64_t ld_x,
+                          int64_t n_dst, int64_t F, float* mean, int64_t ld_mean,
+                          const int32_t* root_idx, float* root, int64_t ld_root,
+                          ngnn_stream_t stream);
+
+/* ---- K-AGG-T: transpose (CSC) segment sum, backward of K-AGG ----
+ *   dx[j,:] = gate_j * ( sum_{q in [colptr_t[j],colptr_t[j+1])} dmean_scaled[row_t[q],:]
+ *                        + (j < n_root ? dx_root[j,:] : 0) )                         for j < n_src
+ * dmean_scaled already carries the 1/max(deg,1) factor (applied by ngnn_sage_dgrad).
+ * gate: if act_ref != NULL, gate_j[f] = act_ref[j,f] > 0 ? act_scale : 0  (ReLU+dropout
+ * backward of the producing layer, folded in); else 1.                                   */
+int32_t ngnn_sage_agg_bwd(const int32_t* colptr_t, const int32_t* row_t, const float* dmean_scaled,
+                          int64_t ld_dmean, int64_t n_src, int64_t F,
+                          const float* dx_root, int64_t ld_root, int64_t n_root,
+                          const float* act_ref, int64_t ld_act, float act_scale,
+                          float* dx, int64_t ld_dx, ngnn_stream_t stream);
+
+/* ---- K-GEMM: fused projection (lin_l + lin_r + bias [+ReLU +dropout]) ----
+ *   out[i,o] = drop( act( sum_f a_l[i,f]*w_l[o,f] + sum_f a_r[i,f]*w_r[o,f] + bias[o] ) )
+ * a_l (the mean) or a_r (the root rows) may be NULL to drop that term; bias may be NULL.
+ * w_l, w_r are PyG-layout weights [O,F] (ld = F).  Dropout: inverted, keep-mask from a
+ * counter-based Philox stream keyed (seed, offset, element index); drop_p = 0 disables.
+ * Tensor-core path (tcgen05, 3xTF32 split => fp32-grade accuracy) when F%4==0 and the
+ * operands are 16-byte aligned, SIMT fp32 path otherwise; `path` (host, may be NULL)
+ * receives 1 for the tcgen05 path, 0 for SIMT.                                          */
+int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar,
+                           const float* w_l, const float* w_r, const float* bias,
+                           int64_t n, int64_t F, int64_t O, int32_t act,
+                           float drop_p, uint64_t seed, uint64_t offset,
+                           float* out, int64_t ld_out, int32_t* path, ngnn_stream_t stream);
+
+/* ---- K-DGRAD: data gradients of the projection ----
+ *   dmean_scaled[i,f] = (1/max(deg_i,1)) * sum_o dy[i,o]*w_l[o,f]     (deg from rowptr; rowptr NULL => 1)
+ *   dx_root[i,f]      =                   sum_o dy[i,o]*w_r[o,f]
+ * Either output may be NULL.                                                              */
+int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r,
+                        const int32_t* rowptr, int64_t n, int64_t F, int64_t O,
+                        float* dmean_scaled, int64_t ld_dmean, float* dx_root, int64_t ld_root,
+                        ngnn_stream_t stream);
+
+/* ---- K-WGRAD: weight / bias gradients ----
+ *   dw_l[o,f] (+)= sum_i dy[i,o]*a_l[i,f];  dw_r[o,f] (+)= sum_i dy[i,o]*a_r[i,f];  db[o] (+)= sum_i dy[i,o]
+ * Split over the long n dimension into fixed slices reduced in a fixed order
+ * (deterministic, atomic-free).  accumulate != 0 adds into the outputs.                  */
+size_t  ngnn_sage_wgrad_workspace_bytes(int64_t n, int64_t F, int64_t O);
+int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al,
+                        const float* a_r, int64_t ld_ar, int64_t n, int64_t F, int64_t O,
+                        float* dw_l, float* dw_r, float* db, int32_t accumulate,
+                        void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* Elementwise backward of ReLU + inverted dropout given the saved post-activation output:
+ *   dz = dh * (h > 0 ? scale : 0)          (scale = 1/(1-p); dropped and negative entries have h == 0) */
+int32_t ngnn_act_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h, int64_t n, int64_t O,
+                     float scale, float* dz, int64_t ld_dz, ngnn_stream_t stream);
+
+/* ---- loss (F.cross_entropy on the seed rows, reference src/pipeline.py:155-165) ----
+ * Mean softmax cross-entropy over bs rows against `target`; one launch produces
+ *   stats[0] += mean loss, stats[1] += #(argmax == y_true)  (y_true NULL => skipped)
+ *   dlogits[i,c] = (softmax_ic - [c==target_i]) * grad_scale / bs                          */
+int32_t ngnn_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true,
+                        int64_t bs, int64_t C, float grad_scale, float* stats /*[2]*/,
+                        float* dlogits, int64_t ld_d, ngnn_stream_t stream);
+
+/* ---- optimizer (torch.optim.Adam(lr), reference src/models/model.py:67-69) ----
+ * One fused pass over a flat parameter bucket; step_count is the 1-based step t held in a
+ * device int64 (so a captured graph can be replayed): the kernel reads *step_dev, and the
+ * thread (0,0) increments it when advance_step != 0.                                         */
+int32_t ngnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float lr, float beta1, float beta2, float eps, float weight_decay,
+                       float grad_scale, int64_t* step_dev, int32_t advance_step, ngnn_stream_t stream);
+
+/* ---- K-SAMPLE / K-RELABEL / K-CSR: fan-out neighbour sampler ----
+ * Graph = CSC by destination: colptr[N+1], row[E] (in-neighbours in stored order).
+ * For hop h = 0..H-1 every node first discovered at hop h-1 (hop 0: the seeds), in
+ * discovery order, draws min(deg,fanout[h]) distinct in-neighbour positions (all of them,
+ * in stored order, when deg <= fanout[h]; fanout[h] draws with replacement when replace!=0
+ * and deg>0).  Draws come from Philox4x32-10 keyed (seed, epoch) with counter
+ * (node global id, hop, batch_idx, draw/4), so a block depends only on
+ * (seed, epoch, batch_idx, seeds) — not on the GPU count or launch geometry.
+ * Newly seen neighbours get local ids in first-seen order (seeds are 0..bs-1).
+ * Outputs (capacity = the worst case given by ngnn_sample_capacity):
+ *   n_id[n]      global id of local node i
+ *   rowptr[n+1]  CSR by destination over ALL n local nodes (last-hop nodes have empty rows)
+ *   col[e]       local source id per edge;  col_global[e] the same in global ids
+ *   e_pos[e]     position of the sampled edge in row[] (maps to PyG's e_id through the CSC perm)
+ *   counts[2*(H+1)] device int32: counts[h] = #nodes after hop h-1 (counts[0]=bs, counts[H]=n),
+ *                counts[H+1+h] = #edges after hop h-1 (counts[H+1]=0, counts[2H+1]=e)
+ * The workspace holds two N-sized maps that must be initialised ONCE with
+ * ngnn_sample_workspace_init and are restored by every call.  Seeds must be distinct.
+ * Bit-exact target: oracle/sampler_oracle.c (same Philox, sequential).                      */
+int32_t ngnn_sample_capacity(int32_t bs, const int32_t* fanouts /*(host)[H]*/, int32_t H, int64_t N,
+                             int64_t* max_nodes, int64_t* max_edges);
+size_t  ngnn_sample_workspace_bytes(int64_t N, int32_t bs, const int32_t* fanouts /*(host)*/, int32_t H);
+int32_t ngnn_sample_workspace_init(void* ws, size_t ws_bytes, int64_t N, ngnn_stream_t stream);
+int32_t ngnn_sample_block(const int32_t* colptr, const int32_t* row, int64_t N,
+                          const int64_t* seeds, int32_t bs, const int32_t* fanouts /*(host)[H]*/, int32_t H,
+                          int32_t replace, uint64_t seed, uint32_t epoch, uint32_t batch_idx,
+                          int32_t* n_id, int32_t* rowptr, int32_t* col, int32_t* col_global, int32_t* e_pos,
+                          int32_t* counts, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGNN_B200_H */

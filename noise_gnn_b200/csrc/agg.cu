@@ -1,0 +1,232 @@
+// agg.cu — K-AGG / K-AGG-T: atomic-free CSR segment reductions over fp32 feature rows.
+//
+// Forward  (SAGEConv mean aggregation, PyG ops K1-K3 in SURVEY §2.3; reference call site
+//           src/models/layers/sage.py:34):    mean[i] = 1/max(deg_i,1) * sum_p x[col[p]]
+// Backward (transpose segment sum, K9-K10):   dx[j]   = gate_j * (sum_q dmean[row_t[q]] + dx_root[j])
+//
+// One group of G lanes (G = 8/16/32, picked from the row width) owns one output row, so the
+// reduction needs no atomics and its summation order is fixed (deterministic).  Feature rows are
+// read as 128-bit vectors, coalesced across the group; up to 4 neighbour rows x VPL vectors are
+// in flight per lane.  The segment's indices are loaded once, coalesced, by the group and
+// broadcast with warp shuffles.  HBM-bound: algorithmic bytes = 4F*(distinct sources) + 4e +
+// 4(n_dst+1) + 4F*n_dst.
+#include "common.cuh"
+
+namespace ngnn {
+
+struct AggParams {
+  const int32_t* ptr;      // rowptr (fwd) / colptr_t (bwd), [n_rows+1]
+  const int32_t* idx;      // col (fwd) / row_t (bwd), [e]
+  const float* x;          // source rows
+  int64_t ld_x;
+  int64_t n_rows;
+  int64_t F;
+  float* out;
+  int64_t ld_out;
+  int32_t mean;            // 1: scale by 1/max(deg,1)
+  const float* add;        // optional rows added for i < n_add (bwd: dx_root)
+  int64_t ld_add;
+  int64_t n_add;
+  const float* act_ref;    // optional gate: out *= (act_ref > 0 ? act_scale : 0)
+  int64_t ld_act;
+  float act_scale;
+  const int32_t* root_idx; // optional fused root gather (fwd): root[i] = x[root_idx[i]]
+  float* root;
+  int64_t ld_root;
+};
+
+__device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) k_seg_reduce_v4(AggParams p) {
+  constexpr int GROUPS_PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);                 // lane within group
+  const int gw = lane / G;                       // group within warp
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gw * G));
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t row = warp * GROUPS_PER_WARP + gw;
+  if (row >= p.n_rows) return;
+
+  const int F4 = (int)(p.F >> 2);
+  const int beg = __ldg(p.ptr + row), end = __ldg(p.ptr + row + 1);
+  const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
+
+  for (int c0 = 0; c0 < F4; c0 += G * VPL) {
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int base = beg; base < end; base += G) {
+      const int cnt = min(G, end - base);
+      const int my = (gl < cnt) ? __ldg(p.idx + base + gl) : 0;
+      for (int j = 0; j < cnt; j += 4) {
+        // up to 4 neighbour rows in flight; out-of-range slots re-read row j (harmless) and are masked
+        int s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] = __shfl_sync(gmask, my, min(j + u, cnt - 1), G);
+        float4 v4[4][VPL];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)s[u] * p.ld_x);
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int c = c0 + gl + v * G;
+            v4[u][v] = (c < F4 && j + u < cnt) ? ldg_nc_f4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) f4_add(acc[v], v4[u][v]);
+      }
+    }
+
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = c0 + gl + v * G;
+      if (c >= F4) continue;
+      float4 r = acc[v];
+      r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+      if (p.add != nullptr && row < p.n_add) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.add + row * p.ld_add) + c);
+        f4_add(r, a);
+      }
+      if (p.act_ref != nullptr) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p.act_ref + row * p.ld_act) + c);
+        r.x = h.x > 0.f ? r.x * p.act_scale : 0.f;
+        r.y = h.y > 0.f ? r.y * p.act_scale : 0.f;
+        r.z = h.z > 0.f ? r.z * p.act_scale : 0.f;
+        r.w = h.w > 0.f ? r.w * p.act_scale : 0.f;
+      }
+      reinterpret_cast<float4*>(p.out + row * p.ld_out)[c] = r;
+    }
+  }
+
+  if (p.root_idx != nullptr) {
+    const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)__ldg(p.root_idx + row) * p.ld_x);
+    float4* dst = reinterpret_cast<float4*>(p.root + row * p.ld_root);
+    for (int c = gl; c < F4; c += G) dst[c] = ldg_nc_f4(src + c);
+  }
+}
+
+// Scalar variant for rows that are not 16-byte addressable (F % 4 != 0, e.g. 1433 or 767).
+template <int VPL>
+__global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= p.n_rows) return;
+  const int F = (int)p.F;
+  const int beg = __ldg(p.ptr + row), end = __ldg(p.ptr + row + 1);
+  const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
+
+  for (int c0 = 0; c0 < F; c0 += 32 * VPL) {
+    float acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = 0.f;
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      const int my = (lane < cnt) ? __ldg(p.idx + base + lane) : 0;
+      for (int j = 0; j < cnt; j += 2) {
+        const int s0 = __shfl_sync(0xffffffffu, my, j);
+        const int s1 = __shfl_sync(0xffffffffu, my, min(j + 1, cnt - 1));
+        const float* r0 = p.x + (int64_t)s0 * p.ld_x;
+        const float* r1 = p.x + (int64_t)s1 * p.ld_x;
+        float a[VPL], b[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = c0 + lane + v * 32;
+          a[v] = (c < F) ? __ldg(r0 + c) : 0.f;
+          b[v] = (c < F && j + 1 < cnt) ? __ldg(r1 + c) : 0.f;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) { acc[v] += a[v]; acc[v] += b[v]; }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = c0 + lane + v * 32;
+      if (c >= F) continue;
+      float r = acc[v] * scale;
+      if (p.add != nullptr && row < p.n_add) r += __ldg(p.add + row * p.ld_add + c);
+      if (p.act_ref != nullptr) r = __ldg(p.act_ref + row * p.ld_act + c) > 0.f ? r * p.act_scale : 0.f;
+      p.out[row * p.ld_out + c] = r;
+    }
+  }
+  if (p.root_idx != nullptr) {
+    const float* src = p.x + (int64_t)__ldg(p.root_idx + row) * p.ld_x;
+    float* dst = p.root + row * p.ld_root;
+    for (int c = lane; c < F; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
+template <int G, int VPL>
+static void launch_v4(const AggParams& p, cudaStream_t st) {
+  constexpr int T = 256;
+  const int64_t rows_per_block = (T / 32) * (32 / G);
+  k_seg_reduce_v4<G, VPL><<<(unsigned)ceil_div(p.n_rows, rows_per_block), T, 0, st>>>(p);
+}
+
+static int32_t run_agg(const AggParams& p, cudaStream_t st) {
+  if (p.n_rows == 0 || p.F == 0) return NGNN_OK;
+  bool vec = (p.F % 4 == 0) && (p.ld_x % 4 == 0) && (p.ld_out % 4 == 0) && is_aligned(p.x, 16) && is_aligned(p.out, 16);
+  if (p.add) vec = vec && (p.ld_add % 4 == 0) && is_aligned(p.add, 16);
+  if (p.act_ref) vec = vec && (p.ld_act % 4 == 0) && is_aligned(p.act_ref, 16);
+  if (p.root_idx) vec = vec && (p.ld_root % 4 == 0) && is_aligned(p.root, 16);
+  if (vec) {
+    const int64_t F4 = p.F / 4;
+    if (F4 <= 8) launch_v4<8, 1>(p, st);
+    else if (F4 <= 16) launch_v4<16, 1>(p, st);
+    else if (F4 <= 32) launch_v4<32, 1>(p, st);
+    else if (F4 <= 64) launch_v4<32, 2>(p, st);
+    else if (F4 <= 128) launch_v4<32, 4>(p, st);
+    else launch_v4<32, 8>(p, st);
+  } else {
+    const unsigned grid = (unsigned)ceil_div(p.n_rows * 32, 256);
+    if (p.F <= 128) k_seg_reduce_scalar<4><<<grid, 256, 0, st>>>(p);
+    else k_seg_reduce_scalar<8><<<grid, 256, 0, st>>>(p);
+  }
+  NGNN_LAUNCH_CHECK();
+  return NGNN_OK;
+}
+
+}  // namespace ngnn
+
+using namespace ngnn;
+
+extern "C" {
+
+int32_t ngnn_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const float* x, int64_t ld_x, int64_t n_dst,
+                          int64_t F, float* mean, int64_t ld_mean, const int32_t* root_idx, float* root,
+                          int64_t ld_root, ngnn_stream_t stream) {
+  NGNN_REQUIRE(n_dst >= 0 && F >= 0, NGNN_E_INVALID, "agg_fwd: negative size");
+  if (n_dst == 0 || F == 0) return NGNN_OK;
+  NGNN_REQUIRE(rowptr && x && mean, NGNN_E_INVALID, "agg_fwd: null pointer");
+  NGNN_REQUIRE(ld_x >= F && ld_mean >= F, NGNN_E_INVALID, "agg_fwd: leading dimension < F");
+  NGNN_REQUIRE(root_idx == nullptr || (root != nullptr && ld_root >= F), NGNN_E_INVALID, "agg_fwd: root buffer missing");
+  AggParams p{};
+  p.ptr = rowptr; p.idx = col; p.x = x; p.ld_x = ld_x; p.n_rows = n_dst; p.F = F;
+  p.out = mean; p.ld_out = ld_mean; p.mean = 1;
+  p.root_idx = root_idx; p.root = root; p.ld_root = ld_root;
+  return run_agg(p, as_stream(stream));
+}
+
+int32_t ngnn_sage_agg_bwd(const int32_t* colptr_t, const int32_t* row_t, const float* dmean_scaled, int64_t ld_dmean,
+                          int64_t n_src, int64_t F, const float* dx_root, int64_t ld_root, int64_t n_root,
+                          const float* act_ref, int64_t ld_act, float act_scale, float* dx, int64_t ld_dx,
+                          ngnn_stream_t stream) {
+  NGNN_REQUIRE(n_src >= 0 && F >= 0 && n_root >= 0, NGNN_E_INVALID, "agg_bwd: negative size");
+  if (n_src == 0 || F == 0) return NGNN_OK;
+  NGNN_REQUIRE(colptr_t && dmean_scaled && dx, NGNN_E_INVALID, "agg_bwd: null pointer");
+  NGNN_REQUIRE(ld_dmean >= F && ld_dx >= F, NGNN_E_INVALID, "agg_bwd: leading dimension < F");
+  NGNN_REQUIRE(dx_root == nullptr || ld_root >= F, NGNN_E_INVALID, "agg_bwd: ld_root < F");
+  NGNN_REQUIRE(act_ref == nullptr || ld_act >= F, NGNN_E_INVALID, "agg_bwd: ld_act < F");
+  AggParams p{};
+  p.ptr = colptr_t; p.idx = row_t; p.x = dmean_scaled; p.ld_x = ld_dmean; p.n_rows = n_src; p.F = F;
+  p.out = dx; p.ld_out = ld_dx; p.mean = 0;
+  p.add = dx_root; p.ld_add = ld_root; p.n_add = dx_root ? n_root : 0;
+  p.act_ref = act_ref; p.ld_act = ld_act; p.act_scale = act_scale;
+  return run_agg(p, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// common.cuh — shared helpers for libngnn_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/ngnn_b200.h"
+
+namespace ngnn {
+
+// thread-local error message (read through ngnn_last_error)
+int32_t set_error(int32_t code, const char* fmt, ...);
+
+#define NGNN_REQUIRE(cond, code, ...)                                        \
+  do {                                                                       \
+    if (!(cond)) return ::ngnn::set_error((code), __VA_ARGS__);              \
+  } while (0)
+
+#define NGNN_CUDA(call)                                                      \
+  do {                                                                       \
+    cudaError_t _e = (call);                                                 \
+    if (_e != cudaSuccess)                                                   \
+      return ::ngnn::set_error(NGNN_E_CUDA, "%s failed: %s (%s:%d)", #call,  \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);  \
+  } while (0)
+
+// every kernel launch in the library is followed by NGNN_LAUNCH_CHECK(), which also counts it
+// (ngnn_launch_count); library primitives (cub) add their launches with count_launches().
+void count_launches(int n);
+
+#define NGNN_LAUNCH_CHECK()                                                  \
+  do {                                                                       \
+    ::ngnn::count_launches(1);                                               \
+    cudaError_t _e = cudaPeekAtLastError();                                  \
+    if (_e != cudaSuccess)                                                   \
+      return ::ngnn::set_error(NGNN_E_CUDA, "kernel launch failed: %s (%s:%d)", \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);  \
+  } while (0)
+
+static inline cudaStream_t as_stream(ngnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter-based: the same (key, counter)
+// gives the same 4 words on host and device.  oracle/sampler_oracle.c carries an
+// independent restatement used to pin the sampler bit-exactly.
+// ---------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// 128-bit read-only global load that does not pollute L1 (streamed gathers)
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+}  // namespace ngnn

@@ -1,0 +1,176 @@
+// gemm.cu — C-ABI entry points of the dense half of SAGEConv: K-GEMM (forward projection,
+// PyG ops K4-K8 of SURVEY §2.3), K-DGRAD and K-WGRAD (K11).  Reference call site of the op
+// being replaced: torch_geometric.nn.SAGEConv.forward via src/models/layers/sage.py:34.
+//
+// Dispatch: the tcgen05/TMA path (gemm_tc.cuh, 3xTF32 split for fp32-grade accuracy) when the
+// operands are TMA-addressable (F % 4 == 0, 16-byte aligned bases and leading dimensions),
+// the SIMT fp32 path (gemm_simt.cuh) otherwise.  Both are device code in this library; there
+// is no host fallback.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace ngnn {
+
+static int32_t wgrad_splits(int64_t n, int64_t F, int64_t O) {
+  const int64_t tiles = ceil_div(O, SG_BM) * ceil_div(F, SG_BN);
+  int64_t s = ceil_div(4 * kNumSMs, tiles);            // aim for ~4 CTAs per SM
+  const int64_t max_s = ceil_div(n, 8 * SG_BK);          // at least 8 k-tiles per slice
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 1024) s = 1024;
+  return (int32_t)s;
+}
+static int32_t colsum_slices(int64_t n) {
+  int64_t s = ceil_div(n, 256);
+  if (s > 512) s = 512;
+  if (s < 1) s = 1;
+  return (int32_t)s;
+}
+
+}  // namespace ngnn
+
+using namespace ngnn;
+
+extern "C" {
+
+int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
+                           const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
+                           float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, int32_t* path,
+                           ngnn_stream_t stream) {
+  NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "gemm_fwd: negative size");
+  NGNN_REQUIRE(act == NGNN_ACT_NONE || act == NGNN_ACT_RELU, NGNN_E_INVALID, "gemm_fwd: unknown activation %d", act);
+  NGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, NGNN_E_INVALID, "gemm_fwd: dropout p=%f outside [0,1)", (double)drop_p);
+  if (path) *path = 0;
+  if (n == 0 || O == 0) return NGNN_OK;
+  NGNN_REQUIRE(out && ld_out >= O, NGNN_E_INVALID, "gemm_fwd: bad output");
+  NGNN_REQUIRE(a_l == nullptr || w_l != nullptr, NGNN_E_INVALID, "gemm_fwd: a_l without w_l");
+  NGNN_REQUIRE(a_r == nullptr || w_r != nullptr, NGNN_E_INVALID, "gemm_fwd: a_r without w_r");
+  NGNN_REQUIRE(a_l == nullptr || ld_al >= F, NGNN_E_INVALID, "gemm_fwd: ld_al < F");
+  NGNN_REQUIRE(a_r == nullptr || ld_ar >= F, NGNN_E_INVALID, "gemm_fwd: ld_ar < F");
+  cudaStream_t st = as_stream(stream);
+
+  int32_t rc = tc_gemm_fwd(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out,
+                           nullptr, st);
+  if (rc == NGNN_OK) { if (path) *path = 1; return NGNN_OK; }
+  if (rc != NGNN_E_UNSUPPORTED) return rc;
+
+  SimtGemmParams p{};
+  if (a_l) { p.A1 = {a_l, ld_al, 1}; p.B1 = {w_l, F, 1}; p.K1 = F; }
+  if (a_r) { p.A2 = {a_r, ld_ar, 1}; p.B2 = {w_r, F, 1}; p.K2 = F; }
+  p.M = n; p.N = O; p.C = out; p.ldc = ld_out; p.bias = bias; p.act = act; p.drop_p = drop_p;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+  p.off_lo = (uint32_t)offset; p.off_hi = (uint32_t)(offset >> 32);
+  return launch_simt_gemm(p, 1, st);
+}
+
+int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
+                        int64_t n, int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root,
+                        int64_t ld_root, ngnn_stream_t stream) {
+  NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "dgrad: negative size");
+  if (n == 0 || F == 0) return NGNN_OK;
+  NGNN_REQUIRE(dy && ld_dy >= O, NGNN_E_INVALID, "dgrad: bad dy");
+  NGNN_REQUIRE(dmean_scaled == nullptr || (w_l && ld_dmean >= F), NGNN_E_INVALID, "dgrad: bad dmean output");
+  NGNN_REQUIRE(dx_root == nullptr || (w_r && ld_root >= F), NGNN_E_INVALID, "dgrad: bad dx_root output");
+  cudaStream_t st = as_stream(stream);
+  // out[i,f] = sum_o dy[i,o] * W[o,f]  : A = dy (K = O contiguous), B(n=f,k=o) = W[o*F + f]
+  if (dmean_scaled) {
+    int32_t rc = tc_gemm_dgrad(dy, ld_dy, w_l, rowptr, n, F, O, dmean_scaled, ld_dmean, st);
+    if (rc == NGNN_E_UNSUPPORTED) {
+      SimtGemmParams p{};
+      p.A1 = {dy, ld_dy, 1}; p.B1 = {w_l, 1, F}; p.K1 = O;
+      p.M = n; p.N = F; p.C = dmean_scaled; p.ldc = ld_dmean; p.rowptr_scale = rowptr;
+      rc = launch_simt_gemm(p, 1, st);
+    }
+    if (rc != NGNN_OK) return rc;
+  }
+  if (dx_root) {
+    int32_t rc = tc_gemm_dgrad(dy, ld_dy, w_r, nullptr, n, F, O, dx_root, ld_root, st);
+    if (rc == NGNN_E_UNSUPPORTED) {
+      SimtGemmParams p{};
+      p.A1 = {dy, ld_dy, 1}; p.B1 = {w_r, 1, F}; p.K1 = O;
+      p.M = n; p.N = F; p.C = dx_root; p.ldc = ld_root;
+      rc = launch_simt_gemm(p, 1, st);
+    }
+    if (rc != NGNN_OK) return rc;
+  }
+  return NGNN_OK;
+}
+
+size_t ngnn_sage_wgrad_workspace_bytes(int64_t n, int64_t F, int64_t O) {
+  if (n <= 0 || F < 0 || O <= 0) return 256;
+  const size_t s = (size_t)wgrad_splits(n, F, O);
+  const size_t c = (size_t)colsum_slices(n);
+  return align_up(s * (size_t)O * (size_t)F * sizeof(float), 256) + align_up(c * (size_t)O * sizeof(float), 256) + 256;
+}
+
+int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r,
+                        int64_t ld_ar, int64_t n, int64_t F, int64_t O, float* dw_l, float* dw_r, float* db,
+                        int32_t accumulate, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "wgrad: negative size");
+  if (O == 0) return NGNN_OK;
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {  // empty block: gradients are zero
+    if (!accumulate) {
+      if (dw_l && F) NGNN_CUDA(cudaMemsetAsync(dw_l, 0, (size_t)O * F * sizeof(float), st));
+      if (dw_r && F) NGNN_CUDA(cudaMemsetAsync(dw_r, 0, (size_t)O * F * sizeof(float), st));
+      if (db) NGNN_CUDA(cudaMemsetAsync(db, 0, (size_t)O * sizeof(float), st));
+    }
+    return NGNN_OK;
+  }
+  NGNN_REQUIRE(dy && ld_dy >= O, NGNN_E_INVALID, "wgrad: bad dy");
+  NGNN_REQUIRE(dw_l == nullptr || (a_l && ld_al >= F), NGNN_E_INVALID, "wgrad: dw_l without a_l");
+  NGNN_REQUIRE(dw_r == nullptr || (a_r && ld_ar >= F), NGNN_E_INVALID, "wgrad: dw_r without a_r");
+  NGNN_REQUIRE(ws && ws_bytes >= ngnn_sage_wgrad_workspace_bytes(n, F, O), NGNN_E_WORKSPACE,
+               "wgrad: workspace too small (%zu < %zu)", ws_bytes, ngnn_sage_wgrad_workspace_bytes(n, F, O));
+  const int32_t S = wgrad_splits(n, F, O);
+  float* part = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  float* cpart = part + align_up((size_t)S * O * F * sizeof(float), 256) / sizeof(float);
+
+  // dW[o,f] = sum_i dy[i,o] * a[i,f] : A(m=o,k=i) = dy[i*ld+o], B(n=f,k=i) = a[i*ld+f]
+  const float* as[2] = {a_l, a_r};
+  const int64_t lds[2] = {ld_al, ld_ar};
+  float* dws[2] = {dw_l, dw_r};
+  for (int w = 0; w < 2; ++w) {
+    if (!dws[w] || F == 0) continue;
+    int32_t rc = tc_gemm_wgrad(dy, ld_dy, as[w], lds[w], n, F, O, dws[w], accumulate, part, st);
+    if (rc == NGNN_OK) continue;
+    if (rc != NGNN_E_UNSUPPORTED) return rc;
+    SimtGemmParams p{};
+    p.A1 = {dy, 1, ld_dy}; p.B1 = {as[w], 1, lds[w]}; p.K1 = n;
+    p.M = O; p.N = F; p.ldc = F;
+    if (S == 1 && !accumulate) {
+      p.C = dws[w]; p.split_stride = 0;
+      rc = launch_simt_gemm(p, 1, st);
+      if (rc != NGNN_OK) return rc;
+    } else {
+      p.C = part; p.split_stride = O * F;
+      rc = launch_simt_gemm(p, S, st);
+      if (rc != NGNN_OK) return rc;
+      k_reduce_partials<<<(unsigned)ceil_div(O * F, 256), 256, 0, st>>>(part, O * F, S, O * F, dws[w], accumulate);
+      NGNN_LAUNCH_CHECK();
+    }
+  }
+  if (db) {
+    const int32_t Cs = colsum_slices(n);
+    const int64_t rows = ceil_div(n, Cs);
+    dim3 grid((unsigned)ceil_div(O, 128), (unsigned)Cs);
+    k_colsum_partial<<<grid, 128, 0, st>>>(dy, ld_dy, n, O, rows, cpart);
+    NGNN_LAUNCH_CHECK();
+    k_reduce_partials<<<(unsigned)ceil_div(O, 256), 256, 0, st>>>(cpart, O, Cs, O, db, accumulate);
+    NGNN_LAUNCH_CHECK();
+  }
+  return NGNN_OK;
+}
+
+int32_t ngnn_act_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h, int64_t n, int64_t O, float scale,
+                     float* dz, int64_t ld_dz, ngnn_stream_t stream) {
+  NGNN_REQUIRE(n >= 0 && O >= 0, NGNN_E_INVALID, "act_bwd: negative size");
+  if (n == 0 || O == 0) return NGNN_OK;
+  NGNN_REQUIRE(dh && h && dz, NGNN_E_INVALID, "act_bwd: null pointer");
+  k_act_bwd<<<(unsigned)ceil_div(n * O, 256), 256, 0, as_stream(stream)>>>(dh, ld_dh, h, ld_h, n, O, scale, dz, ld_dz);
+  NGNN_LAUNCH_CHECK();
+  return NGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+"""Data / NeighborLoader — drop-in for ``torch_geometric.loader.NeighborLoader`` as the reference uses it.
+
+Reference call sites: constructed at src/pipeline.py:75-92 (train loader: ``input_nodes=train idx``,
+``num_neighbors=config['nbr_neighbors']``, ``batch_size``, ``shuffle=True``, ``num_workers=1``,
+``persistent_workers=True``; eval loader: ``input_nodes`` = all splits / None, batch 4092/4096),
+re-created per run at :211-219, iterated at :152 and src/models/layers/sage.py:49, ``len(loader)`` at
+:170; batch attributes used: ``.to(device)``, ``.x``, ``.edge_index``, ``.y``, ``.yhn``, ``.n_id``,
+``.batch_size`` (:153-157, :118).
+
+B200-first: instead of CPU worker processes that sample, slice ``x[n_id]`` and ship ~180 MB per batch
+over PCIe, the graph (CSC, int32), the feature table and every ``[N, ...]`` node
+attribute are uploaded ONCE and stay resident in HBM; each batch is sampled on the GPU by
+``ngnn_sample_block`` (counter-based Philox, sync-free on the device) and comes back already on the
+device, so ``batch.to(device)`` is a no-op.  The only per-step host->device traffic is the seed ids.
+``num_workers`` / ``persistent_workers`` are accepted and ignored (there are no worker processes).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+
+class Data:
+    """Minimal PyG ``Data``-like attribute bag: x, edge_index, y plus ad-hoc node attributes
+    (the reference attaches ``data.yhn`` after loading, src/pipeline.py:72,208)."""
+
+    def __init__(self, x=None, edge_index=None, y=None, **kwargs):
+        self.x, self.edge_index, self.y = x, edge_index, y
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self) -> int:
+        if self.x is not None:
+            return int(self.x.size(0))
+        if "_num_nodes" in self.__dict__:
+            return int(self.__dict__["_num_nodes"])
+        return int(self.edge_index.max()) + 1
+
+    @num_nodes.setter
+    def num_nodes(self, v):
+        self.__dict__["_num_nodes"] = int(v)
+
+    @property
+    def num_edges(self) -> int:
+        return int(self.edge_index.size(1))
+
+    @property
+    def num_features(self) -> int:
+        return int(self.x.size(1))
+
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if not k.startswith("_") and v is not None]
+
+    def to(self, device, **kw):
+        for k in self.keys():
+            v = getattr(self, k)
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device, **kw))
+        return self
+
+    def __repr__(self):
+        parts = [f"{k}={list(v.shape) if torch.is_tensor(v) else v}" for k, v in ((k, getattr(self, k)) for k in self.keys())]
+        return f"Data({', '.join(parts)})"
+
+
+class Batch:
+    """One sampled message-flow block, resident on the device.
+
+    ``x``, ``edge_index``, ``e_id`` and the node attributes are materialised lazily on first access
+    (``x`` by a row gather from the resident feature table, ``edge_index`` as PyG's int64 COO with the
+    CSR block attached so SAGEConv does not re-sort it)."""
+
+    def __init__(self, loader: "NeighborLoader", block: ops.Block, n_id32: torch.Tensor, e_pos: Optional[torch.Tensor],
+                 batch_size: int, input_id: torch.Tensor):
+        self._loader, self.block = loader, block
+        self._n_id32, self._e_pos = n_id32, e_pos
+        self.batch_size = int(batch_size)
+        self.input_id = input_id
+        self.num_nodes, self.num_edges = block.n_rows, block.e
+        hn, he = block.hop_nodes, block.hop_edges
+        self.num_sampled_nodes = [hn[0]] + [hn[i + 1] - hn[i] for i in range(len(hn) - 1)]
+        self.num_sampled_edges = [he[i + 1] - he[i] for i in range(len(he) - 1)]
+        self._cache = {}
+
+    @property
+    def device(self):
+        return self._n_id32.device
+
+    def to(self, device, *args, **kwargs):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("a noise_gnn_b200 Batch lives on the GPU that sampled it; .to(cpu) is not supported "
+                               "(copy the individual tensors you need)")
+        return self
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        cache = self.__dict__["_cache"]
+        if name in cache:
+            return cache[name]
+        loader = self.__dict__["_loader"]
+        if name == "x":
+            v = ops.gather_rows(loader.x, self._n_id32, self.num_nodes)
+        elif name == "edge_index":
+            v = ops.csr_to_coo(self.block.rowptr, self.block.col, self.block.n_rows, self.block.e)
+            v._ngnn_block = self.block
+        elif name == "n_id":
+            v = self._n_id32.long()
+        elif name == "e_id":
+            if self._e_pos is None:
+                raise AttributeError("e_id was not requested (NeighborLoader(..., return_e_id=True))")
+            v = loader.csc_perm.index_select(0, self._e_pos.long()).long()
+        elif name in loader.node_attrs:
+            v = loader.node_attrs[name].index_select(0, self.n_id)
+        else:
+            raise AttributeError(name)
+        cache[name] = v
+        return v
+
+    def __repr__(self):
+        return (f"Batch(num_nodes={self.num_nodes}, num_edges={self.num_edges}, batch_size={self.batch_size}, "
+                f"hops={self.num_sampled_nodes})")
+
+
+class NeighborLoader:
+    def __init__(self, data, num_neighbors: Sequence[int], input_nodes=None, batch_size: int = 1,
+                 shuffle: bool = False, replace: bool = False, num_workers: int = 0,
+                 persistent_workers: bool = False, drop_last: bool = False, device=None, seed: int = 1232,
+                 rank: int = 0, world_size: int = 1, return_e_id: bool = False, **kwargs):
+        unsupported = {k: v for k, v in kwargs.items() if k in ("disjoint", "temporal_strategy", "time_attr",
+                       "weight_attr", "subgraph_type", "transform", "filter_per_worker") and v not in (None, False, "directional")}
+        if unsupported:
+            raise NotImplementedError(f"NeighborLoader options not used by the reference: {sorted(unsupported)}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("noise_gnn_b200.NeighborLoader samples on the GPU; no CUDA device is available "
+                               "(there is no CPU fallback)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.num_neighbors = [int(f) for f in num_neighbors]
+        if any(f < 1 for f in self.num_neighbors):
+            raise NotImplementedError("num_neighbors entries must be >= 1 (-1 = all neighbours is not used by the reference)")
+        self.batch_size, self.shuffle, self.replace, self.drop_last = int(batch_size), bool(shuffle), bool(replace), bool(drop_last)
+        self.seed, self.rank, self.world_size = int(seed), int(rank), int(world_size)
+        self.return_e_id = return_e_id
+        self.epoch = 0
+        self.data = data
+        N = data.num_nodes
+        self.num_nodes = N
+
+        with torch.cuda.device(self.device):
+            # --- resident graph: CSC by destination (stable => in-neighbours keep stored order) ---
+            ei = data.edge_index.to(self.device)
+            blk = ops.coo_to_csr(ei, N)
+            self.colptr, self.row, self.csc_perm = blk.rowptr, blk.col, blk.perm
+            self.num_edges = blk.e
+            del ei
+            # --- resident feature table and node attributes (anything shaped [N, ...]) ---
+            self.x = None
+            self.node_attrs = {}
+            for k in data.keys():
+                v = getattr(data, k)
+                if not torch.is_tensor(v) or k == "edge_index" or v.dim() == 0 or v.size(0) != N:
+                    continue
+                if k == "x":
+                    self.x = v.to(self.device, dtype=torch.float32).contiguous()
+                else:
+                    self.node_attrs[k] = v.to(self.device)
+            # --- seeds ---
+            if input_nodes is None:
+                nodes = torch.arange(N, dtype=torch.int64)
+            else:
+                nodes = torch.as_tensor(input_nodes).cpu()
+                if nodes.dtype == torch.bool:
+                    nodes = nodes.nonzero().view(-1)
+                nodes = nodes.to(torch.int64).view(-1)
+            self.input_nodes = nodes
+            # --- sampler capacities and workspace ---
+            L = _lib.load()
+            self._fan = (ctypes.c_int32 * len(self.num_neighbors))(*self.num_neighbors)
+            mn, me = ctypes.c_int64(), ctypes.c_int64()
+            _lib.call("ngnn_sample_capacity", self.batch_size, self._fan, len(self.num_neighbors), N,
+                      ctypes.byref(mn), ctypes.byref(me))
+            self.max_nodes, self.max_edges = mn.value, me.value
+            nbytes = L.ngnn_sample_workspace_bytes(N, self.batch_size, self._fan, len(self.num_neighbors))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.call("ngnn_sample_workspace_init", ops._ptr(self._ws), self._ws.numel(), N, ops._stream())
+
+    # ------------------------------------------------------------------ batching
+    @property
+    def num_batches_global(self) -> int:
+        n = len(self.input_nodes)
+        return n // self.batch_size if self.drop_last else math.ceil(n / self.batch_size)
+
+    def __len__(self) -> int:
+        return math.ceil(self.num_batches_global / self.world_size)
+
+    def epoch_permutation(self, epoch: int) -> torch.Tensor:
+        """Rank-agnostic seed order for an epoch: a pure function of (seed, epoch)."""
+        if not self.shuffle:
+            return self.input_nodes
+        g = torch.Generator(device="cpu")
+        g.manual_seed((self.seed * 1000003 + epoch) & 0x7FFFFFFFFFFFFFFF)
+        return self.input_nodes[torch.randperm(len(self.input_nodes), generator=g)]
+
+    def batch_seeds(self, order: torch.Tensor, global_batch_idx: int) -> torch.Tensor:
+        b = global_batch_idx % max(self.num_batches_global, 1)      # wrap-around pads the last DP round
+        return order[b * self.batch_size:(b + 1) * self.batch_size]
+
+    def sample(self, seeds: torch.Tensor, epoch: int = 0, batch_idx: int = 0) -> Batch:
+        """Sample one block for explicit seeds (host or device int64)."""
+        H = len(self.num_neighbors)
+        with torch.cuda.device(self.device):
+            if not seeds.is_cuda:
+                seeds = seeds.pin_memory().to(self.device, non_blocking=True) if seeds.numel() else seeds.to(self.device)
+            seeds = seeds.to(torch.int64).contiguous()
+            bs = seeds.numel()
+            if bs == 0:
+                raise ValueError("cannot sample an empty seed batch")
+            if bs > self.batch_size:
+                raise ValueError(f"{bs} seeds exceed the loader's batch_size {self.batch_size}")
+            dev = self.device
+            n_id = torch.empty(self.max_nodes, dtype=torch.int32, device=dev)
+            rowptr = torch.empty(self.max_nodes + 1, dtype=torch.int32, device=dev)
+            col = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
+            colg = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
+            epos = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev) if self.return_e_id else None
+            counts = torch.empty(2 * (H + 1), dtype=torch.int32, device=dev)
+            with ops._timed("sample"):
+              _lib.call("ngnn_sample_block", ops._ptr(self.colptr), ops._ptr(self.row), self.num_nodes, ops._ptr(seeds), bs,
+                      self._fan, H, int(self.replace), self.seed & (2**64 - 1), epoch & 0xFFFFFFFF, batch_idx & 0xFFFFFFFF,
+                      ops._ptr(n_id), ops._ptr(rowptr), ops._ptr(col), ops._ptr(colg), ops._ptr(epos), ops._ptr(counts),
+                      ops._ptr(self._ws), self._ws.numel(), ops._stream())
+            c = counts.cpu().tolist()                      # the one host read per batch: block extents
+            hop_nodes, hop_edges = c[:H + 1], c[H + 1:]
+            n, e = hop_nodes[-1], hop_edges[-1]
+            block = ops.Block(rowptr[:n + 1], col[:e], n, e, hop_nodes=hop_nodes, hop_edges=hop_edges,
+                              col_global=colg[:e], n_id=n_id[:n])
+            return Batch(self, block, n_id[:n], None if epos is None else epos[:e], bs, seeds)
+
+    def __iter__(self):
+        epoch = self.epoch
+        self.epoch += 1
+        order = self.epoch_permutation(epoch)
+        for i in range(len(self)):
+            g = i * self.world_size + self.rank
+            yield self.sample(self.batch_seeds(order, g), epoch=epoch, batch_idx=g % max(self.num_batches_global, 1))

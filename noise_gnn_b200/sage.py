@@ -1,0 +1,149 @@
+"""SAGE — the reference's GraphSAGE network (src/models/layers/sage.py:6-78) on B200-native kernels.
+
+Same constructor, attributes and methods as the reference module
+(``SAGE(in_size, hidden_size, out_size, num_layers, dropout=0.5, use_bn=False)``, ``.convs``,
+``.reset_parameters()``, ``.forward(x, edge_index)``, ``.inference(x_all, subgraph_loader, device)``) and
+the same state_dict keys (``convs.{i}.lin_l.weight|bias``, ``convs.{i}.lin_r.weight``), so it can be
+swapped in where ``NGNN.init_network`` builds the reference module (src/models/model.py:44-50).
+(The unmodified reference ``sage.py`` also runs on these kernels through ``compat/torch_geometric``.)
+
+Two execution modes:
+
+* ``forward(x, edge_index)`` — reference-exact: every layer on the whole block, ReLU then dropout
+  between layers (torch's generator supplies the dropout mask, as in the reference).
+* ``forward_batch(batch)`` — the B200-first path for blocks that come from our NeighborLoader: layer
+  ``l`` of ``L`` only computes the rows within ``L-l`` hops of the seeds (prefixes of the block, exact
+  for the seed rows the caller keeps — SURVEY §8 trimming note), layer 1 aggregates straight from the
+  resident feature table (no ``x[n_id]`` materialisation), and ReLU + dropout are fused into the GEMM
+  epilogue with a counter-based Philox mask.  Returns ``[batch_size, out_size]``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .conv import SAGEConv, _block_cache
+
+NGNN_ACT_NONE, NGNN_ACT_RELU = 0, 1
+
+
+class _SAGELayerFunction(torch.autograd.Function):
+    """One trimmed SAGE layer with fused epilogue.
+
+    x_src: rows the edges read (a previous layer's output, or the resident feature table when
+    `table_mode`), block prefix (n_dst rows, e_limit edges).  act/dropout fused in the GEMM; the saved
+    post-activation output gates the backward (h > 0 <=> pre-activation > 0 and kept)."""
+
+    @staticmethod
+    def forward(ctx, x_src, w_l, b_l, w_r, block, n_dst, e_limit, n_src, table_mode, act, drop_p, seed, offset, tag):
+        if table_mode:   # aggregate from the resident table by global ids, gather the root rows in the same launch
+            mean, root = ops.agg_fwd(block.rowptr, block.col_global, x_src, n_dst, root_idx=block.n_id, tag="agg_" + tag)
+        else:
+            mean, root = ops.agg_fwd(block.rowptr, block.col, x_src, n_dst, tag="agg_" + tag), x_src
+        out = ops.gemm_fwd(mean, root, w_l, w_r, b_l, n_dst, act=act, drop_p=drop_p, seed=seed, offset=offset,
+                           tag="gemm_" + tag)
+        ctx.save_for_backward(mean, root, w_l, w_r, out if act or drop_p > 0 else None)
+        ctx.block, ctx.n_dst, ctx.e_limit, ctx.n_src = block, n_dst, e_limit, n_src
+        ctx.table_mode, ctx.act, ctx.drop_p, ctx.tag = table_mode, act, drop_p, tag
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        mean, root, w_l, w_r, out = ctx.saved_tensors
+        block, n_dst = ctx.block, ctx.n_dst
+        if out is not None:
+            dy = ops.act_bwd(dy, out, 1.0 / (1.0 - ctx.drop_p))
+        F_ = mean.size(1)
+        dw_l, dw_r, db = ops.wgrad(dy, mean, root, n_dst, F_, tag="wgrad_" + ctx.tag)
+        dx = None
+        if ctx.needs_input_grad[0] and not ctx.table_mode:
+            dmean, droot = ops.dgrad(dy, w_l, w_r, block.rowptr, n_dst, tag="dgrad_" + ctx.tag)
+            colptr_t, row_t = block.transpose(ctx.e_limit, ctx.n_src)
+            dx = ops.agg_bwd(colptr_t, row_t, dmean, ctx.n_src, dx_root=droot, n_root=n_dst, tag="aggT_" + ctx.tag)
+        return (dx, dw_l, db, dw_r) + (None,) * 10
+
+
+class SAGE(torch.nn.Module):
+    def __init__(self, in_size, hidden_size, out_size, num_layers, dropout=0.5, use_bn=False):
+        super().__init__()
+        self.num_layers, self.dropout, self.use_bn = num_layers, dropout, use_bn
+        dims = [in_size] + [hidden_size] * (num_layers - 1) + [out_size]
+        self.convs = torch.nn.ModuleList(SAGEConv(dims[i], dims[i + 1]) for i in range(num_layers))
+        if use_bn:   # dead in the reference (no caller passes use_bn=True); kept for API parity, torch BN
+            self.bn1 = torch.nn.BatchNorm1d(in_size)
+            self.bn2 = torch.nn.BatchNorm1d(hidden_size)
+        self._drop_calls = 0
+        self.drop_seed = 1232
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+
+    # ---- reference-exact mode ------------------------------------------------------------
+    def forward(self, x, edge_index):
+        if self.use_bn:
+            x = self.bn1(x)
+        last = self.num_layers - 1
+        for i, conv in enumerate(self.convs):
+            x = conv(x, edge_index)
+            if i != last:
+                x = x.relu()
+                if self.use_bn:
+                    x = self.bn2(x)
+                x = F.dropout(x, p=self.dropout, training=self.training)
+        return x
+
+    # ---- trimmed, fused mode ---------------------------------------------------------------
+    @staticmethod
+    def layer_extents(block: ops.Block, num_layers: int):
+        """Per layer (n_dst, e_limit, n_src): rows within L-l hops of the seeds, the edges into them, and
+        the rows those edges read — all prefixes of the block (SURVEY §8 trimming note)."""
+        hn, he = block.hop_nodes, block.hop_edges
+        H = len(hn) - 1
+        ext = []
+        for layer in range(1, num_layers + 1):
+            d = num_layers - layer
+            ext.append((hn[min(d, H)], he[min(d + 1, H)], hn[min(d + 1, H)]))
+        return ext
+
+    def forward_batch(self, batch, x_table=None):
+        """Trimmed fused forward on a Batch of our NeighborLoader; returns logits of the seed rows."""
+        if self.use_bn:
+            raise NotImplementedError("use_bn is dead code in the reference; the fused path does not cover it")
+        block = batch.block
+        table = x_table if x_table is not None else batch._loader.x
+        p = float(self.dropout) if self.training else 0.0
+        self._drop_calls += 1
+        ext = self.layer_extents(block, self.num_layers)
+        h = table
+        last = self.num_layers - 1
+        for i, conv in enumerate(self.convs):
+            n_dst, e_limit, n_src = ext[i]
+            act = NGNN_ACT_RELU if i != last else NGNN_ACT_NONE
+            h = _SAGELayerFunction.apply(h, conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, block, n_dst, e_limit,
+                                         n_src, i == 0, act, p if i != last else 0.0, self.drop_seed,
+                                         self._drop_calls * self.num_layers + i, f"l{i + 1}")
+        return h[: batch.batch_size]
+
+    # ---- layer-wise inference (reference sage.py:42-58) -----------------------------------------
+    @torch.no_grad()
+    def inference(self, x_all, subgraph_loader, device=None, return_cpu: bool = True):
+        """Layer by layer over all input nodes of `subgraph_loader`, with the loader's sampled fan-outs
+        (as the reference does).  Activations stay on the GPU between layers; per batch only the seed
+        rows are computed (only hop-1 edges reach them)."""
+        dev = subgraph_loader.device
+        x_all = x_all.to(dev, dtype=torch.float32)
+        last = self.num_layers - 1
+        for i, conv in enumerate(self.convs):
+            xs = []
+            for batch in subgraph_loader:
+                blk = batch.block
+                bs, e1 = batch.batch_size, blk.hop_edges[1]
+                x = ops.gather_rows(x_all, batch._n_id32, blk.hop_nodes[1])
+                mean = ops.agg_fwd(blk.rowptr, blk.col, x, bs)
+                out = ops.gemm_fwd(mean, x, conv.lin_l.weight, conv.lin_r.weight, conv.lin_l.bias, bs,
+                                   act=NGNN_ACT_RELU if i != last else NGNN_ACT_NONE)
+                xs.append(out)
+            x_all = torch.cat(xs, dim=0)
+        return x_all.cpu() if return_cpu else x_all

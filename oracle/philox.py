@@ -1,0 +1,47 @@
+"""numpy Philox4x32-10 — TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Restates the generator of Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3"
+(SC'11), the counter-based RNG the CUDA sampler and the fused dropout use.  Pinned in
+tests/test_oracle.py against the Random123 known-answer vectors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Vectorised over numpy arrays of counters (broadcastable); returns four uint32 arrays."""
+    c0, c1, c2, c3 = np.broadcast_arrays(*(np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3)))
+    k0 &= 0xFFFFFFFF
+    k1 &= 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
+        n1 = p1 & MASK
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
+        n3 = p0 & MASK
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def dropout_keep_mask(n_rows: int, n_cols: int, p: float, seed: int, offset: int) -> np.ndarray:
+    """Keep-mask of the fused dropout in K-GEMM's epilogue (noise_gnn_b200/csrc/gemm_simt.cuh):
+    element (m, c) is kept iff word[c % 4] of philox(counter=(m, c//4, offset_lo, offset_hi),
+    key=(seed_lo, seed_hi)) >= floor(p * 2^32)."""
+    thr = min(max(int(p * 4294967296.0), 0), 4294967295)
+    cq = (n_cols + 3) // 4
+    m = np.arange(n_rows, dtype=np.uint64)[:, None]
+    q = np.arange(cq, dtype=np.uint64)[None, :]
+    words = philox4x32_10(m, q, offset & 0xFFFFFFFF, (offset >> 32) & 0xFFFFFFFF,
+                          seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    w = np.stack(words, axis=-1).reshape(n_rows, cq * 4)[:, :n_cols]
+    return w >= np.uint32(thr)

@@ -1,0 +1,157 @@
+"""CPU tests: the oracle against published / exact / independent answers (no GPU needed)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox, sage_oracle, sampler, structure
+
+GOLD = json.loads((Path(__file__).parent / "golden" / "sage_known_answer.json").read_text())
+
+
+def test_philox_random123_known_answers():
+    # kat_vectors of Random123 (philox4x32, 10 rounds)
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    import ctypes
+    lib = sampler._load()
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(*ctr, *key)
+        assert tuple(int(g) for g in got) == want
+        c = (ctypes.c_uint32 * 4)(*ctr); k = (ctypes.c_uint32 * 2)(*key); o = (ctypes.c_uint32 * 4)()
+        lib.ngnn_oracle_philox(c, k, o)
+        assert tuple(o) == want
+
+
+def test_sageconv_oracle_matches_exact_known_answer():
+    g = GOLD
+    conv = sage_oracle.SAGEConvRef(3, 2, dtype=torch.float64)
+    with torch.no_grad():
+        conv.lin_l.weight.copy_(torch.tensor(g["w_l"])); conv.lin_l.bias.copy_(torch.tensor(g["b_l"]))
+        conv.lin_r.weight.copy_(torch.tensor(g["w_r"]))
+    x = torch.tensor(g["x"], dtype=torch.float64, requires_grad=True)
+    ei = torch.tensor([g["src"], g["dst"]])
+    out = conv(x, ei)
+    assert torch.allclose(out, torch.tensor(g["out"], dtype=torch.float64), rtol=0, atol=1e-12)
+    assert torch.allclose(sage_oracle.mean_aggregate(x, ei), torch.tensor(g["mean"], dtype=torch.float64), atol=1e-12)
+    (out * torch.tensor(g["grad_out"], dtype=torch.float64)).sum().backward()
+    for got, key in ((conv.lin_l.weight.grad, "d_w_l"), (conv.lin_r.weight.grad, "d_w_r"),
+                     (conv.lin_l.bias.grad, "d_b_l"), (x.grad, "d_x")):
+        assert torch.allclose(got, torch.tensor(g[key], dtype=torch.float64), rtol=0, atol=1e-12), key
+
+
+def test_sageconv_oracle_fp32_vs_fp64_calibrates_tolerance():
+    torch.manual_seed(0)
+    n, e, F, O = 500, 3000, 100, 47
+    x = torch.randn(n, F, dtype=torch.float64)
+    ei = torch.randint(0, n, (2, e))
+    c64 = sage_oracle.SAGEConvRef(F, O, dtype=torch.float64)
+    c32 = sage_oracle.SAGEConvRef(F, O)
+    c32.load_state_dict({k: v.float() for k, v in c64.state_dict().items()})
+    o64, o32 = c64(x, ei), c32(x.float(), ei)
+    rel = (o32.double() - o64).abs().max() / o64.abs().max()
+    assert rel < 1e-5   # the north-star tolerance is achievable in plain fp32
+
+
+def test_structure_oracle_known_answer():
+    src = np.array([1, 3, 1, 2, 4, 0, 2, 5, 3]); dst = np.array([0, 1, 0, 2, 2, 3, 4, 4, 0])
+    rowptr, col, perm = structure.coo_to_csr(src, dst, 6)
+    assert rowptr.tolist() == [0, 3, 4, 6, 7, 9, 9]
+    assert col.tolist() == [1, 1, 3, 3, 2, 4, 0, 2, 5]
+    assert perm.tolist() == [0, 2, 8, 1, 3, 4, 5, 6, 7]
+    colptr_t, row_t, perm_t = structure.csr_transpose(rowptr, col, 6)
+    assert colptr_t.tolist() == [0, 1, 3, 5, 7, 8, 9]
+    assert row_t.tolist() == [3, 0, 0, 2, 4, 0, 1, 2, 4]
+    assert np.array_equal(structure.csr_to_coo(rowptr, col), np.stack([src[perm], dst[perm]]))
+    # empty graph
+    rp, c, p = structure.coo_to_csr(np.zeros(0, int), np.zeros(0, int), 4)
+    assert rp.tolist() == [0] * 5 and len(c) == 0
+
+
+def _random_csc(n, m, seed):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n, m); dst = rng.integers(0, n, m)
+    rowptr, col, _ = structure.coo_to_csr(src, dst, n)
+    return rowptr, col
+
+
+@pytest.mark.parametrize("replace", [False, True])
+def test_c_sampler_matches_python_twin(replace):
+    colptr, row = _random_csc(300, 4000, 1)
+    seeds = np.random.default_rng(2).permutation(300)[:17]
+    for fan in ([3], [15, 10, 5], [25, 1], [2, 2, 2, 2]):
+        a = sampler.sample_block(colptr, row, seeds, fan, replace, seed=1232, epoch=3, batch_idx=7)
+        b = sampler.sample_block_py(colptr, row, seeds, fan, replace, seed=1232, epoch=3, batch_idx=7)
+        for f in ("n_id", "rowptr", "col", "col_global", "e_pos", "node_counts", "edge_counts"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (fan, f)
+
+
+def check_block_validity(blk, colptr, row, seeds, fanouts, replace=False):
+    """North-star validity: true neighbours, fan-out caps, no duplicate positions, seeds first, unique n_id."""
+    n, e = blk.n, blk.e
+    assert np.array_equal(blk.n_id[:len(seeds)], np.asarray(seeds, dtype=np.int32))
+    assert len(np.unique(blk.n_id)) == n
+    assert blk.rowptr[0] == 0 and blk.rowptr[-1] == e and np.all(np.diff(blk.rowptr) >= 0)
+    assert np.array_equal(blk.n_id[blk.col], blk.col_global)
+    assert np.array_equal(row[blk.e_pos], blk.col_global)
+    deg_g = np.diff(colptr)
+    for h, fan in enumerate(fanouts):
+        lo = 0 if h == 0 else blk.node_counts[h - 1]
+        hi = blk.node_counts[h]
+        for i in range(lo, hi):
+            v = blk.n_id[i]
+            seg = blk.e_pos[blk.rowptr[i]:blk.rowptr[i + 1]]
+            d = deg_g[v]
+            want = (fan if d > 0 else 0) if replace else min(d, fan)
+            assert len(seg) == want
+            assert np.all((seg >= colptr[v]) & (seg < colptr[v + 1]))         # true in-neighbours of v
+            if not replace:
+                assert len(np.unique(seg)) == len(seg)                         # distinct positions
+                if d <= fan:
+                    assert np.array_equal(seg, np.arange(colptr[v], colptr[v + 1]))   # take-all keeps stored order
+    assert np.all(np.diff(blk.rowptr)[blk.node_counts[len(fanouts) - 1]:] == 0)   # last hop not expanded
+    # first-seen order: new ids appear in increasing order along the edge list
+    first = {}
+    for p, c in enumerate(blk.col):
+        first.setdefault(int(c), p)
+    new_ids = [c for c in sorted(first, key=first.get) if c >= len(seeds)]
+    assert new_ids == sorted(new_ids)
+
+
+def test_sampler_oracle_validity_and_determinism():
+    colptr, row = _random_csc(500, 9000, 5)
+    seeds = np.random.default_rng(6).permutation(500)[:32]
+    for fan, rep in (([15, 10, 5], False), ([4, 4], True), ([30], False)):
+        blk = sampler.sample_block(colptr, row, seeds, fan, rep, seed=1232, epoch=0, batch_idx=0)
+        check_block_validity(blk, colptr, row, seeds, fan, rep)
+        again = sampler.sample_block(colptr, row, seeds, fan, rep, seed=1232, epoch=0, batch_idx=0)
+        assert np.array_equal(blk.col_global, again.col_global)
+        other = sampler.sample_block(colptr, row, seeds, fan, rep, seed=1232, epoch=1, batch_idx=0)
+        if max(fan) < 30:   # fan-out 30 exceeds most degrees here => take-all, nothing random
+            assert not np.array_equal(blk.e_pos, other.e_pos)
+
+
+def test_sampler_oracle_positions_are_uniform():
+    # chi-square on the sampled positions of one high-degree node over many (epoch, batch) keys
+    d, k = 40, 10
+    colptr = np.array([0, d] + [d] * d, dtype=np.int32)
+    row = np.arange(1, d + 1, dtype=np.int32)
+    s = sampler.CSampler(colptr, row)
+    hist = np.zeros(d)
+    trials = 4000
+    for t in range(trials):
+        blk = s.sample(np.array([0]), [k], False, seed=1232, epoch=t, batch_idx=t // 7)
+        hist[blk.e_pos] += 1
+    expect = trials * k / d
+    chi2 = ((hist - expect) ** 2 / expect).sum()
+    assert chi2 < 80.0   # 39 dof: mean 39, 99.99th percentile ~ 78
+
+
+def test_dropout_mask_rate():
+    m = philox.dropout_keep_mask(512, 256, 0.5, seed=1232, offset=9)
+    assert abs(m.mean() - 0.5) < 0.01
+    assert philox.dropout_keep_mask(8, 7, 0.0, 1, 1).all()
