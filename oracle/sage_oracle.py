@@ -105,7 +105,7 @@ def train_step(model: SAGERef, optimizer, x, edge_index, y, yhn, batch_size: int
     y = y[:batch_size].squeeze()
     yhn = yhn[:batch_size].squeeze()
     loss = F.cross_entropy(out, yhn)
-    total_loss = float(loss)
+    total_loss = float(loss.detach())
     total_correct = int(out.argmax(dim=-1).eq(y).sum())
     optimizer.zero_grad()
     loss.backward()
