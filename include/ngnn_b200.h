@@ -107,20 +107,25 @@ int32_t ngnn_sage_agg_bwd(const int32_t* colptr_t, const int32_t* row_t, const f
  * Tensor-core path (tcgen05, 3xTF32 split => fp32-grade accuracy) when F%4==0 and the
  * operands are 16-byte aligned, SIMT fp32 path otherwise; `path` (host, may be NULL)
  * receives 1 for the tcgen05 path, 0 for SIMT.                                          */
+size_t  ngnn_sage_gemm_workspace_bytes(int64_t F, int64_t O);   /* split-weight planes of the tcgen05 path */
 int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar,
                            const float* w_l, const float* w_r, const float* bias,
                            int64_t n, int64_t F, int64_t O, int32_t act,
                            float drop_p, uint64_t seed, uint64_t offset,
-                           float* out, int64_t ld_out, int32_t* path, ngnn_stream_t stream);
+                           float* out, int64_t ld_out, int32_t* path,
+                           void* ws, size_t ws_bytes, ngnn_stream_t stream);
+/* 0 = automatic dispatch (default), 1 = force the SIMT fp32 kernels (tests / A-B timing). */
+int32_t ngnn_set_gemm_path(int32_t mode);
 
 /* ---- K-DGRAD: data gradients of the projection ----
  *   dmean_scaled[i,f] = (1/max(deg_i,1)) * sum_o dy[i,o]*w_l[o,f]     (deg from rowptr; rowptr NULL => 1)
  *   dx_root[i,f]      =                   sum_o dy[i,o]*w_r[o,f]
  * Either output may be NULL.                                                              */
+size_t  ngnn_sage_dgrad_workspace_bytes(int64_t F, int64_t O);
 int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r,
                         const int32_t* rowptr, int64_t n, int64_t F, int64_t O,
                         float* dmean_scaled, int64_t ld_dmean, float* dx_root, int64_t ld_root,
-                        ngnn_stream_t stream);
+                        void* ws, size_t ws_bytes, ngnn_stream_t stream);
 
 /* ---- K-WGRAD: weight / bias gradients ----
  *   dw_l[o,f] (+)= sum_i dy[i,o]*a_l[i,f];  dw_r[o,f] (+)= sum_i dy[i,o]*a_r[i,f];  db[o] (+)= sum_i dy[i,o]

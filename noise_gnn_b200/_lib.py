@@ -27,9 +27,13 @@ SIGNATURES = {
     "ngnn_sage_agg_fwd": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, c_int64, _P]),
     "ngnn_sage_agg_bwd": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64,
                                     c_float, _P, c_int64, _P]),
+    "ngnn_sage_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ngnn_sage_gemm_fwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, c_int32,
-                                     c_float, c_uint64, c_uint64, _P, c_int64, _P, _P]),
-    "ngnn_sage_dgrad": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P]),
+                                     c_float, c_uint64, c_uint64, _P, c_int64, _P, _P, c_size_t, _P]),
+    "ngnn_set_gemm_path": (c_int32, [c_int32]),
+    "ngnn_sage_dgrad_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ngnn_sage_dgrad": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P,
+                                  c_size_t, _P]),
     "ngnn_sage_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "ngnn_sage_wgrad": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P,
                                   c_int32, _P, c_size_t, _P]),

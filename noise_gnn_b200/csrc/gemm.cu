@@ -12,6 +12,8 @@
 
 namespace ngnn {
 
+static int g_force_simt = 0;   // ngnn_set_gemm_path: 1 => always take the SIMT kernels (tests, A/B timing)
+
 static int32_t wgrad_splits(int64_t n, int64_t F, int64_t O) {
   const int64_t tiles = ceil_div(O, SG_BM) * ceil_div(F, SG_BN);
   int64_t s = ceil_div(4 * kNumSMs, tiles);            // aim for ~4 CTAs per SM
@@ -37,7 +39,7 @@ extern "C" {
 int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
                            const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
                            float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, int32_t* path,
-                           ngnn_stream_t stream) {
+                           void* ws, size_t ws_bytes, ngnn_stream_t stream) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "gemm_fwd: negative size");
   NGNN_REQUIRE(act == NGNN_ACT_NONE || act == NGNN_ACT_RELU, NGNN_E_INVALID, "gemm_fwd: unknown activation %d", act);
   NGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, NGNN_E_INVALID, "gemm_fwd: dropout p=%f outside [0,1)", (double)drop_p);
@@ -50,10 +52,12 @@ int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, in
   NGNN_REQUIRE(a_r == nullptr || ld_ar >= F, NGNN_E_INVALID, "gemm_fwd: ld_ar < F");
   cudaStream_t st = as_stream(stream);
 
-  int32_t rc = tc_gemm_fwd(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out,
-                           nullptr, st);
-  if (rc == NGNN_OK) { if (path) *path = 1; return NGNN_OK; }
-  if (rc != NGNN_E_UNSUPPORTED) return rc;
+  if (!g_force_simt) {
+    int32_t rc = tc_gemm_fwd(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out,
+                             ws, ws_bytes, st);
+    if (rc == NGNN_OK) { if (path) *path = 1; return NGNN_OK; }
+    if (rc != NGNN_E_UNSUPPORTED) return rc;
+  }
 
   SimtGemmParams p{};
   if (a_l) { p.A1 = {a_l, ld_al, 1}; p.B1 = {w_l, F, 1}; p.K1 = F; }
@@ -66,7 +70,7 @@ int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, in
 
 int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
                         int64_t n, int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root,
-                        int64_t ld_root, ngnn_stream_t stream) {
+                        int64_t ld_root, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "dgrad: negative size");
   if (n == 0 || F == 0) return NGNN_OK;
   NGNN_REQUIRE(dy && ld_dy >= O, NGNN_E_INVALID, "dgrad: bad dy");
@@ -74,28 +78,36 @@ int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const 
   NGNN_REQUIRE(dx_root == nullptr || (w_r && ld_root >= F), NGNN_E_INVALID, "dgrad: bad dx_root output");
   cudaStream_t st = as_stream(stream);
   // out[i,f] = sum_o dy[i,o] * W[o,f]  : A = dy (K = O contiguous), B(n=f,k=o) = W[o*F + f]
+  if (!g_force_simt) {
+    int32_t rc = tc_gemm_dgrad(dy, ld_dy, w_l, w_r, rowptr, n, F, O, dmean_scaled, ld_dmean, dx_root, ld_root, ws,
+                               ws_bytes, st);
+    if (rc != NGNN_E_UNSUPPORTED) return rc;
+  }
   if (dmean_scaled) {
-    int32_t rc = tc_gemm_dgrad(dy, ld_dy, w_l, rowptr, n, F, O, dmean_scaled, ld_dmean, st);
-    if (rc == NGNN_E_UNSUPPORTED) {
-      SimtGemmParams p{};
-      p.A1 = {dy, ld_dy, 1}; p.B1 = {w_l, 1, F}; p.K1 = O;
-      p.M = n; p.N = F; p.C = dmean_scaled; p.ldc = ld_dmean; p.rowptr_scale = rowptr;
-      rc = launch_simt_gemm(p, 1, st);
-    }
+    SimtGemmParams p{};
+    p.A1 = {dy, ld_dy, 1}; p.B1 = {w_l, 1, F}; p.K1 = O;
+    p.M = n; p.N = F; p.C = dmean_scaled; p.ldc = ld_dmean; p.rowptr_scale = rowptr;
+    int32_t rc = launch_simt_gemm(p, 1, st);
     if (rc != NGNN_OK) return rc;
   }
   if (dx_root) {
-    int32_t rc = tc_gemm_dgrad(dy, ld_dy, w_r, nullptr, n, F, O, dx_root, ld_root, st);
-    if (rc == NGNN_E_UNSUPPORTED) {
-      SimtGemmParams p{};
-      p.A1 = {dy, ld_dy, 1}; p.B1 = {w_r, 1, F}; p.K1 = O;
-      p.M = n; p.N = F; p.C = dx_root; p.ldc = ld_root;
-      rc = launch_simt_gemm(p, 1, st);
-    }
+    SimtGemmParams p{};
+    p.A1 = {dy, ld_dy, 1}; p.B1 = {w_r, 1, F}; p.K1 = O;
+    p.M = n; p.N = F; p.C = dx_root; p.ldc = ld_root;
+    int32_t rc = launch_simt_gemm(p, 1, st);
     if (rc != NGNN_OK) return rc;
   }
   return NGNN_OK;
 }
+
+int32_t ngnn_set_gemm_path(int32_t mode) {
+  NGNN_REQUIRE(mode == 0 || mode == 1, NGNN_E_INVALID, "set_gemm_path: mode must be 0 (auto) or 1 (force SIMT)");
+  g_force_simt = mode;
+  return NGNN_OK;
+}
+
+size_t ngnn_sage_gemm_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_fwd_ws_bytes(F, O) : 256; }
+size_t ngnn_sage_dgrad_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_dgrad_ws_bytes(F, O) : 256; }
 
 size_t ngnn_sage_wgrad_workspace_bytes(int64_t n, int64_t F, int64_t O) {
   if (n <= 0 || F < 0 || O <= 0) return 256;
@@ -133,7 +145,7 @@ int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_
   float* dws[2] = {dw_l, dw_r};
   for (int w = 0; w < 2; ++w) {
     if (!dws[w] || F == 0) continue;
-    int32_t rc = tc_gemm_wgrad(dy, ld_dy, as[w], lds[w], n, F, O, dws[w], accumulate, part, st);
+    int32_t rc = g_force_simt ? NGNN_E_UNSUPPORTED : tc_gemm_wgrad(dy, ld_dy, as[w], lds[w], n, F, O, dws[w], accumulate, part, st);
     if (rc == NGNN_OK) continue;
     if (rc != NGNN_E_UNSUPPORTED) return rc;
     SimtGemmParams p{};

@@ -1,20 +1,505 @@
-// gemm_tc.cuh — tcgen05 / TMA tensor-core path of K-GEMM, K-DGRAD, K-WGRAD (sm_100a).
-// Each entry returns NGNN_E_UNSUPPORTED (without setting an error) when the shape is outside
-// what the tensor-core kernels cover, and the caller falls through to the SIMT kernels.
+// gemm_tc.cuh — tcgen05 / TMA tensor-core path of K-GEMM and K-DGRAD (sm_100a).
+//
+//   D[m, n] = sum_k A1[m,k] * B1[n,k] + sum_k A2[m,k] * B2[n,k]        (both operands K-major)
+//
+// fp32-grade accuracy on the TF32 tensor pipe by the 3xTF32 split (SURVEY §7.3 hard part 1):
+//   x = hi + lo, hi = round-to-nearest of x to 10 mantissa bits, lo = x - hi (exact in fp32);
+//   D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (the dropped lo*lo term is ~2^-22 relative).
+// Weights (B) are split once per call by a tiny prep kernel into a packed K-major workspace
+// [rows, Kpack] (hi and lo planes, K zero-padded to whole 32-float blocks); activations (A) are
+// split in shared memory by the converter warps, in place, right after TMA lands them.
+//
+// One CTA = one 128 x BN output tile (BN = N rounded up to 16, <= 256), 6 warps:
+//   warp 0      TMA producer: per K-block (32 floats = one 128-byte swizzle atom) loads the raw A
+//               tile [128 x 32] and the B_hi / B_lo tiles [BN x 32] (SWIZZLE_128B) into a stage
+//   warp 1      allocates TMEM, issues tcgen05.mma.kind::tf32 (12 per K-block: 4 k-steps x 3 terms),
+//               tcgen05.commit frees the stage / signals the epilogue
+//   warps 2-5   converter (raw A -> hi in place, lo plane) during the main loop, then the epilogue:
+//               tcgen05.ld the fp32 accumulator, + bias, row scale, ReLU, Philox dropout, store.
+// Accumulators live in TMEM (128 lanes x BN fp32 columns).  Partial tiles rely on TMA's zero fill
+// for out-of-bounds rows / columns; stores are bounds-checked.
 #pragma once
 #include "common.cuh"
+#include "gemm_simt.cuh"   // dropout_keep4 / dropout_threshold (the mask definition is shared)
+#include <cuda.h>
 
 namespace ngnn {
 
-static inline int32_t tc_gemm_fwd(const float*, int64_t, const float*, int64_t, const float*, const float*,
-                                  const float*, int64_t, int64_t, int64_t, int32_t, float, uint64_t, uint64_t,
-                                  float*, int64_t, const int32_t*, cudaStream_t) {
-  return NGNN_E_UNSUPPORTED;
+constexpr int TC_BM = 128;            // rows per CTA tile (UMMA M)
+constexpr int TC_BK = 32;             // floats per K-block: 128 bytes = one SWIZZLE_128B atom
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 4;
+constexpr uint32_t TC_SMEM_LIMIT = 227u * 1024u;
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-static inline int32_t tc_gemm_dgrad(const float*, int64_t, const float*, const int32_t*, int64_t, int64_t, int64_t,
-                                    float*, int64_t, cudaStream_t) {
-  return NGNN_E_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// Bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)0 << 16;                       // LBO unused: one swizzle atom along K
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32; // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // LayoutType::SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::tf32: D fp32, A/B tf32, both K-major, shape M x N (x8).
+__host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// hi = x rounded to nearest at mantissa bit 13 (10 explicit bits kept), lo = x - hi (exact)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  const uint32_t u = __float_as_uint(x);
+  hi = __uint_as_float((u + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+// ----------------------------------------------------------------------------- weight prep
+// Packs up to two [R, C] fp32 weight matrices side by side along K into hi / lo planes [R_out, Kpack]:
+//   transpose == 0: out[r, seg*Cpad + c] = W_seg[r, c]           (forward:  B = [W_l | W_r], rows = O, K = F)
+//   transpose == 1: out[seg*Rpad + c, r] = W_seg[r, c]           (dgrad:    B = [W_l^T ; W_r^T], rows = F, K = O)
+// K padding is zero-filled.
+struct PrepParams {
+  const float* w[2];
+  int32_t R, C;          // source rows / cols
+  int32_t transpose;
+  int32_t seg_stride;    // forward: Cpad (k offset of segment 1); dgrad: row offset of segment 1
+  int32_t Kpack;         // leading dimension of the packed planes
+  int32_t rows_out;
+  float *hi, *lo;
+};
+__global__ void k_prep_weights(PrepParams p) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)p.rows_out * p.Kpack;
+  if (idx >= total) return;
+  const int32_t ro = (int32_t)(idx / p.Kpack), ko = (int32_t)(idx - (int64_t)ro * p.Kpack);
+  float v = 0.f;
+  if (!p.transpose) {
+    const int32_t seg = ko / p.seg_stride, c = ko - seg * p.seg_stride;
+    if (seg < 2 && p.w[seg] != nullptr && c < p.C) v = p.w[seg][(int64_t)ro * p.C + c];
+  } else {
+    const int32_t seg = ro / p.seg_stride, c = ro - seg * p.seg_stride;
+    if (seg < 2 && p.w[seg] != nullptr && c < p.C && ko < p.R) v = p.w[seg][(int64_t)ko * p.C + c];
+  }
+  float hi, lo;
+  split_tf32(v, hi, lo);
+  p.hi[idx] = hi;
+  p.lo[idx] = lo;
+}
+
+// ----------------------------------------------------------------------------- main kernel
+struct TcSegment {            // one N range of the packed B matrix and where its output goes
+  float* out;
+  int64_t ld_out;
+  int32_t n_cols;             // valid output columns of this segment
+  int32_t b_row0;             // first row of the segment in the packed B planes
+  int32_t scale_rows;         // 1: scale row m by 1/max(rowptr[m+1]-rowptr[m],1)
+};
+struct TcGemmParams {
+  int32_t M;                  // rows
+  int32_t BN;                 // UMMA N / columns per CTA tile
+  int32_t kblocks1, kblocks2; // K-blocks of operand pair 1 / 2
+  int32_t b_koff2;            // k offset (floats) of pair 2 in the packed B planes
+  int32_t stages;
+  int32_t tiles_per_seg;      // N tiles per segment (grid.y = tiles_per_seg * num_segs)
+  TcSegment seg[2];
+  const float* bias;
+  const int32_t* rowptr;
+  int32_t act;
+  float drop_p;
+  uint32_t seed_lo, seed_hi, off_lo, off_hi;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+          const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const uint32_t a_bytes = TC_BM * TC_BK * 4;                 // 16 KB
+  const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* full_conv = full_raw + TC_MAX_STAGES;
+  uint64_t* empty = full_conv + TC_MAX_STAGES;
+  uint64_t* tmem_full = empty + TC_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t m0 = blockIdx.x * TC_BM;
+  const int32_t seg_id = blockIdx.y / p.tiles_per_seg;
+  const int32_t n_tile = blockIdx.y - seg_id * p.tiles_per_seg;
+  const TcSegment sg = p.seg[seg_id];
+  const int32_t n0 = n_tile * p.BN;                            // first output column of this tile within the segment
+  const int32_t KB = p.kblocks1 + p.kblocks2;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int32_t kb = 0; kb < KB; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full_raw[s], a_bytes + 2 * b_bytes);
+        const bool first = kb < p.kblocks1;
+        const int32_t ka = (first ? kb : kb - p.kblocks1) * TC_BK;
+        const int32_t kbk = first ? ka : p.b_koff2 + ka;
+        tma_load_2d(st, first ? &tmA1 : &tmA2, &full_raw[s], ka, m0);
+        tma_load_2d(st + 2 * a_bytes, &tmBhi, &full_raw[s], kbk, sg.b_row0 + n0);
+        tma_load_2d(st + 2 * a_bytes + b_bytes, &tmBlo, &full_raw[s], kbk, sg.b_row0 + n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_tf32(TC_BM, (uint32_t)p.BN);
+    for (int32_t kb = 0; kb < KB; ++kb) {
+      const int s = kb % p.stages;
+      const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+      mbar_wait(&full_conv[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + 2 * a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint32_t koff = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle atom
+          const uint64_t dah = umma_desc_k_sw128(a_hi + koff), dal = umma_desc_k_sw128(a_lo + koff);
+          const uint64_t dbh = umma_desc_k_sw128(b_hi + koff), dbl = umma_desc_k_sw128(b_lo + koff);
+          umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        }
+        umma_commit(&empty[s]);                      // stage reusable once these MMAs have read it
+        if (kb == KB - 1) umma_commit(tmem_full);    // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== converter warps (2..5) =====================
+    const int t = threadIdx.x - 64;                  // 0..127
+    for (int32_t kb = 0; kb < KB; ++kb) {
+      const int s = kb % p.stages;
+      const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+      mbar_wait(&full_raw[s], ph);
+      float4* hi4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+      float4* lo4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
+#pragma unroll
+      for (int j = 0; j < (TC_BM * TC_BK / 4) / 128; ++j) {
+        const int i = t + 128 * j;
+        const float4 x = hi4[i];
+        float4 h, l;
+        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+        hi4[i] = h;
+        lo4[i] = l;
+      }
+      fence_proxy_async_smem();                      // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_conv[s]);
+    }
+    // ===================== epilogue =====================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int64_t m = (int64_t)m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    float rs = 1.0f;
+    if (sg.scale_rows && p.rowptr != nullptr && row_ok)
+      rs = 1.0f / (float)max(__ldg(p.rowptr + m + 1) - __ldg(p.rowptr + m), 1);
+    const uint32_t thr = dropout_threshold(p.drop_p);
+    const float keep_scale = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    float* orow = sg.out + m * sg.ld_out;
+    const bool vec_ok = ((sg.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
+    for (int32_t c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      const int32_t nb = n0 + c;
+      if (!row_ok || nb >= sg.n_cols) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int32_t n4 = nb + 4 * g;
+        if (n4 >= sg.n_cols) break;
+        float r[4];
+        uint32_t keep = 0xFu;
+        if (p.drop_p > 0.f) keep = dropout_keep4((uint32_t)m, (uint32_t)(n4 >> 2), p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = __uint_as_float(v[4 * g + j]);
+          if (p.bias != nullptr && n4 + j < sg.n_cols) x += __ldg(p.bias + n4 + j);
+          x *= rs;
+          if (p.act == NGNN_ACT_RELU) x = fmaxf(x, 0.f);
+          if (p.drop_p > 0.f) x = ((keep >> j) & 1u) ? x * keep_scale : 0.f;
+          r[j] = x;
+        }
+        if (vec_ok && n4 + 3 < sg.n_cols) {
+          *reinterpret_cast<float4*>(orow + n4) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (n4 + j < sg.n_cols) orow[n4 + j] = r[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 32 floats], SWIZZLE_128B
+static inline bool make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows,
+                                uint32_t box_cols = TC_BK) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static inline bool tma_addressable(const float* p, int64_t ld) { return p != nullptr && is_aligned(p, 16) && (ld % 4 == 0) && ld > 0; }
+
+static inline int32_t round_up_i(int64_t x, int64_t a) { return (int32_t)((x + a - 1) / a * a); }
+
+struct TcPlan {
+  int32_t BN, tiles_per_seg, stages;
+  uint32_t smem_bytes;
+};
+static inline TcPlan tc_plan(int64_t n_cols) {
+  TcPlan pl;
+  pl.BN = n_cols >= 256 ? 256 : round_up_i(n_cols, 16);
+  pl.tiles_per_seg = (int32_t)ceil_div(n_cols, pl.BN);
+  const uint32_t stage = 2u * TC_BM * TC_BK * 4u + 2u * (uint32_t)pl.BN * TC_BK * 4u;
+  int st = (int)((TC_SMEM_LIMIT - 2048u) / stage);
+  pl.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+  pl.smem_bytes = (uint32_t)pl.stages * stage + 1024u /*align*/ + 256u /*barriers*/;
+  return pl;
+}
+
+// workspace: hi + lo planes of the packed weights
+static inline size_t tc_fwd_ws_bytes(int64_t F, int64_t O) {
+  const int64_t Kpack = 2 * (int64_t)round_up_i(F, TC_BK);
+  return 2 * align_up((size_t)O * Kpack * sizeof(float), 256) + 256;
+}
+static inline size_t tc_dgrad_ws_bytes(int64_t F, int64_t O) {
+  const int64_t Kpack = round_up_i(O, TC_BK);
+  const int64_t rows = 2 * (int64_t)round_up_i(F, 16);
+  return 2 * align_up((size_t)rows * Kpack * sizeof(float), 256) + 256;
+}
+
+static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& bh, const CUtensorMap& bl,
+                                const TcGemmParams& p, const TcPlan& pl, int num_segs, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NGNN_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(p.M, TC_BM), (unsigned)(pl.tiles_per_seg * num_segs));
+  k_tc_gemm<<<grid, TC_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, p);
+  NGNN_LAUNCH_CHECK();
+  return NGNN_OK;
+}
+
+// out = drop(act(a_l W_l^T + a_r W_r^T + b)).  Returns NGNN_E_UNSUPPORTED (no error text) when the
+// operands are not TMA-addressable; the caller then uses the SIMT kernel.
+static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
+                                  const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
+                                  float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, void* ws,
+                                  size_t ws_bytes, cudaStream_t st) {
+  if (F % 4 != 0 || F < 4 || n < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+  if (a_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
+  if (a_r && !tma_addressable(a_r, ld_ar)) return NGNN_E_UNSUPPORTED;
+  if (!a_l && !a_r) return NGNN_E_UNSUPPORTED;
+  if (ws == nullptr || ws_bytes < tc_fwd_ws_bytes(F, O) || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
+
+  const int32_t Fpad = round_up_i(F, TC_BK), Kpack = 2 * Fpad;
+  float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  float* lo = hi + align_up((size_t)O * Kpack * sizeof(float), 256) / sizeof(float);
+  PrepParams pp{};
+  pp.w[0] = a_l ? w_l : nullptr; pp.w[1] = a_r ? w_r : nullptr;
+  pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 0; pp.seg_stride = Fpad; pp.Kpack = Kpack; pp.rows_out = (int32_t)O;
+  pp.hi = hi; pp.lo = lo;
+  k_prep_weights<<<(unsigned)ceil_div((int64_t)O * Kpack, 256), 256, 0, st>>>(pp);
+  NGNN_LAUNCH_CHECK();
+
+  const TcPlan pl = tc_plan(O);
+  CUtensorMap tA1, tA2, tBh, tBl;
+  const float* a1 = a_l ? a_l : a_r;
+  const int64_t ld1 = a_l ? ld_al : ld_ar;
+  const bool two = a_l && a_r;
+  bool ok = make_tmap_2d(&tA1, a1, n, F, ld1, TC_BM);
+  ok = ok && make_tmap_2d(&tA2, two ? a_r : a1, n, F, two ? ld_ar : ld1, TC_BM);
+  ok = ok && make_tmap_2d(&tBh, hi, O, Kpack, Kpack, (uint32_t)pl.BN);
+  ok = ok && make_tmap_2d(&tBl, lo, O, Kpack, Kpack, (uint32_t)pl.BN);
+  NGNN_REQUIRE(ok, NGNN_E_CUDA, "gemm_fwd: cuTensorMapEncodeTiled failed");
+
+  TcGemmParams p{};
+  p.M = (int32_t)n; p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
+  p.kblocks1 = Fpad / TC_BK; p.kblocks2 = two ? Fpad / TC_BK : 0;
+  p.b_koff2 = Fpad;
+  if (!a_l) { p.b_koff2 = 0; /* single operand is a_r: its weights sit in segment 1 of the pack */ }
+  p.seg[0] = TcSegment{out, ld_out, (int32_t)O, 0, 0};
+  p.bias = bias; p.act = act; p.drop_p = drop_p;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.off_lo = (uint32_t)offset; p.off_hi = (uint32_t)(offset >> 32);
+  if (!a_l) {
+    // only the root term: read its weights from k offset Fpad of the pack
+    CUtensorMap shifted;
+    ok = make_tmap_2d(&shifted, hi + Fpad, O, Fpad, Kpack, (uint32_t)pl.BN);
+    CUtensorMap shifted_lo;
+    ok = ok && make_tmap_2d(&shifted_lo, lo + Fpad, O, Fpad, Kpack, (uint32_t)pl.BN);
+    NGNN_REQUIRE(ok, NGNN_E_CUDA, "gemm_fwd: cuTensorMapEncodeTiled failed");
+    return tc_launch(tA1, tA2, shifted, shifted_lo, p, pl, 1, st);
+  }
+  return tc_launch(tA1, tA2, tBh, tBl, p, pl, 1, st);
+}
+
+// dmean_scaled = rowscale * (dy W_l), dx_root = dy W_r, both in one launch (two N segments).
+static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
+                                    int64_t n, int64_t F, int64_t O, float* dmean, int64_t ld_dmean, float* droot,
+                                    int64_t ld_root, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n < 1 || F < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+  if (!tma_addressable(dy, ld_dy)) return NGNN_E_UNSUPPORTED;
+  if (ws == nullptr || ws_bytes < tc_dgrad_ws_bytes(F, O) || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
+  if (!dmean && !droot) return NGNN_OK;
+
+  const int32_t Kpack = round_up_i(O, TC_BK), Rpad = round_up_i(F, 16);
+  const int32_t rows = 2 * Rpad;
+  float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  float* lo = hi + align_up((size_t)rows * Kpack * sizeof(float), 256) / sizeof(float);
+  PrepParams pp{};
+  pp.w[0] = dmean ? w_l : nullptr; pp.w[1] = droot ? w_r : nullptr;
+  pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 1; pp.seg_stride = Rpad; pp.Kpack = Kpack; pp.rows_out = rows;
+  pp.hi = hi; pp.lo = lo;
+  k_prep_weights<<<(unsigned)ceil_div((int64_t)rows * Kpack, 256), 256, 0, st>>>(pp);
+  NGNN_LAUNCH_CHECK();
+
+  const TcPlan pl = tc_plan(F);
+  CUtensorMap tA, tBh, tBl;
+  bool ok = make_tmap_2d(&tA, dy, n, O, ld_dy, TC_BM);
+  ok = ok && make_tmap_2d(&tBh, hi, rows, Kpack, Kpack, (uint32_t)pl.BN);
+  ok = ok && make_tmap_2d(&tBl, lo, rows, Kpack, Kpack, (uint32_t)pl.BN);
+  NGNN_REQUIRE(ok, NGNN_E_CUDA, "dgrad: cuTensorMapEncodeTiled failed");
+
+  TcGemmParams p{};
+  p.M = (int32_t)n; p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
+  p.kblocks1 = Kpack / TC_BK; p.kblocks2 = 0; p.b_koff2 = 0;
+  p.rowptr = rowptr;
+  int ns = 0;
+  if (dmean) p.seg[ns++] = TcSegment{dmean, ld_dmean, (int32_t)F, 0, rowptr != nullptr ? 1 : 0};
+  if (droot) p.seg[ns++] = TcSegment{droot, ld_root, (int32_t)F, Rpad, 0};
+  return tc_launch(tA, tA, tBh, tBl, p, pl, ns, st);
+}
+
 static inline int32_t tc_gemm_wgrad(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*,
                                     int32_t, float*, cudaStream_t) {
   return NGNN_E_UNSUPPORTED;

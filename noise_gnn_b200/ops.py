@@ -213,10 +213,12 @@ def gemm_fwd(a_l, a_r, w_l, w_r, bias, n: int, act: int = 0, drop_p: float = 0.0
     w_r = None if w_r is None else w_r.contiguous()
     y = out if out is not None else torch.empty((n, O), dtype=_F32, device=ref.device)
     path = ctypes.c_int32(0)
+    ws = workspaces.get(_lib.load().ngnn_sage_gemm_workspace_bytes(F_, O), ref.device, "gemm")
     with _timed(tag or "gemm_fwd"):
         _lib.call("ngnn_sage_gemm_fwd", _ptr(a_l), _ld(a_l) if a_l is not None else 0, _ptr(a_r),
                   _ld(a_r) if a_r is not None else 0, _ptr(w_l), _ptr(w_r), _ptr(bias), n, F_, O, int(act), float(drop_p),
-                  int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _ptr(y), _ld(y), ctypes.byref(path), _stream())
+                  int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _ptr(y), _ld(y), ctypes.byref(path),
+                  _ptr(ws), ws.numel(), _stream())
     return (y, path.value) if return_path else y
 
 
@@ -228,11 +230,12 @@ def dgrad(dy, w_l, w_r, rowptr, n: int, want_mean: bool = True, want_root: bool 
     dev = dy.device
     dmean = torch.empty((n, F_), dtype=_F32, device=dev) if want_mean else None
     droot = torch.empty((n, F_), dtype=_F32, device=dev) if want_root else None
+    ws = workspaces.get(_lib.load().ngnn_sage_dgrad_workspace_bytes(F_, O), dev, "dgrad")
     with _timed(tag or "dgrad"):
         _lib.call("ngnn_sage_dgrad", _ptr(dy), _ld(dy), _ptr(w_l.contiguous() if w_l is not None else None),
                   _ptr(w_r.contiguous() if w_r is not None else None), _ptr(rowptr), n, F_, O,
                   _ptr(dmean), _ld(dmean) if dmean is not None else 0, _ptr(droot), _ld(droot) if droot is not None else 0,
-                  _stream())
+                  _ptr(ws), ws.numel(), _stream())
     return dmean, droot
 
 
