@@ -35,7 +35,7 @@ def test_version_and_error_string_without_gpu():
     assert rc == -1
     assert "negative" in _lib.last_error()
     with pytest.raises(_lib.NgnnError):
-        _lib.call("ngnn_sage_gemm_fwd", None, 0, None, 0, None, None, None, 4, 4, 4, 7, 0.0, 0, 0, None, 0, None, None)
+        _lib.call("ngnn_sage_gemm_fwd", None, 0, None, 0, None, None, None, 4, 4, 4, 7, 0.0, 0, 0, None, 0, None, None, 0, None)
 
 
 def test_library_contains_sm100a_code_only():

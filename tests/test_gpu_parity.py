@@ -128,18 +128,28 @@ def test_agg_bwd_matches_oracle(dev, F):
 
 # ------------------------------------------------------------------ K-GEMM / K-DGRAD / K-WGRAD
 GEMM_SHAPES = [(1, 4, 3), (130, 100, 256), (700, 256, 47), (257, 128, 40), (300, 1433, 7), (90, 767, 10),
-               (1000, 500, 3), (513, 256, 256), (64, 512, 7)]
+               (1000, 500, 3), (513, 256, 256), (64, 512, 7), (300, 64, 512), (4000, 100, 256)]
+
+
+@pytest.fixture(params=["auto", "simt"])
+def gemm_path(request, dev):
+    """Runs a GEMM test twice: automatic dispatch (tcgen05 where the operands are TMA-addressable) and forced SIMT."""
+    from noise_gnn_b200 import _lib
+    _lib.call("ngnn_set_gemm_path", 1 if request.param == "simt" else 0)
+    yield request.param
+    _lib.call("ngnn_set_gemm_path", 0)
 
 
 @pytest.mark.parametrize("n,F,O", GEMM_SHAPES)
-def test_gemm_fwd_matches_oracle(dev, n, F, O):
+def test_gemm_fwd_matches_oracle(dev, gemm_path, n, F, O):
     from noise_gnn_b200 import ops
     g = torch.Generator().manual_seed(n + F + O)
     a_l, a_r = torch.randn(n, F, generator=g), torch.randn(n + 5, F, generator=g)
     w_l, w_r = torch.randn(O, F, generator=g) / F ** 0.5, torch.randn(O, F, generator=g) / F ** 0.5
     b = torch.randn(O, generator=g)
     want = a_l.double() @ w_l.double().T + a_r[:n].double() @ w_r.double().T + b.double()
-    got = ops.gemm_fwd(a_l.to(dev), a_r.to(dev), w_l.to(dev), w_r.to(dev), b.to(dev), n)
+    got, path = ops.gemm_fwd(a_l.to(dev), a_r.to(dev), w_l.to(dev), w_r.to(dev), b.to(dev), n, return_path=True)
+    assert path == (1 if (gemm_path == "auto" and F % 4 == 0) else 0)     # tcgen05 path is the one that ran
     assert rel_err(got, want) < RTOL
     got_relu = ops.gemm_fwd(a_l.to(dev), a_r.to(dev), w_l.to(dev), w_r.to(dev), b.to(dev), n, act=1)
     assert rel_err(got_relu, want.clamp(min=0)) < RTOL
@@ -148,7 +158,7 @@ def test_gemm_fwd_matches_oracle(dev, n, F, O):
     assert rel_err(got_r, a_r[:n].double() @ w_r.double().T) < RTOL
 
 
-def test_gemm_fused_dropout_mask_is_the_philox_oracle_mask(dev):
+def test_gemm_fused_dropout_mask_is_the_philox_oracle_mask(dev, gemm_path):
     from noise_gnn_b200 import ops
     n, F, O, p = 300, 64, 100, 0.5
     a = torch.randn(n, F); w = torch.randn(O, F) / 8; b = torch.randn(O)
@@ -161,7 +171,7 @@ def test_gemm_fused_dropout_mask_is_the_philox_oracle_mask(dev):
 
 
 @pytest.mark.parametrize("n,F,O", GEMM_SHAPES)
-def test_dgrad_and_wgrad_match_oracle(dev, n, F, O):
+def test_dgrad_and_wgrad_match_oracle(dev, gemm_path, n, F, O):
     from noise_gnn_b200 import ops
     g = torch.Generator().manual_seed(7 * n + F + O)
     dy = torch.randn(n, O, generator=g)
