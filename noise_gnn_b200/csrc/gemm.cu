@@ -109,11 +109,13 @@ int32_t ngnn_set_gemm_path(int32_t mode) {
 size_t ngnn_sage_gemm_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_fwd_ws_bytes(F, O) : 256; }
 size_t ngnn_sage_dgrad_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_dgrad_ws_bytes(F, O) : 256; }
 
+static size_t colsum_ws_bytes(int64_t n, int64_t O) { return align_up((size_t)colsum_slices(n) * (size_t)O * sizeof(float), 256); }
+
 size_t ngnn_sage_wgrad_workspace_bytes(int64_t n, int64_t F, int64_t O) {
   if (n <= 0 || F < 0 || O <= 0) return 256;
-  const size_t s = (size_t)wgrad_splits(n, F, O);
-  const size_t c = (size_t)colsum_slices(n);
-  return align_up(s * (size_t)O * (size_t)F * sizeof(float), 256) + align_up(c * (size_t)O * sizeof(float), 256) + 256;
+  const size_t simt = align_up((size_t)wgrad_splits(n, F, O) * (size_t)O * (size_t)F * sizeof(float), 256);
+  const size_t tc = F >= 4 ? tc_wgrad_ws_bytes(n, F, O) : 0;
+  return colsum_ws_bytes(n, O) + (simt > tc ? simt : tc) + 512;
 }
 
 int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r,
@@ -135,32 +137,38 @@ int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_
   NGNN_REQUIRE(dw_r == nullptr || (a_r && ld_ar >= F), NGNN_E_INVALID, "wgrad: dw_r without a_r");
   NGNN_REQUIRE(ws && ws_bytes >= ngnn_sage_wgrad_workspace_bytes(n, F, O), NGNN_E_WORKSPACE,
                "wgrad: workspace too small (%zu < %zu)", ws_bytes, ngnn_sage_wgrad_workspace_bytes(n, F, O));
-  const int32_t S = wgrad_splits(n, F, O);
-  float* part = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
-  float* cpart = part + align_up((size_t)S * O * F * sizeof(float), 256) / sizeof(float);
+  float* cpart = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  float* part = cpart + colsum_ws_bytes(n, O) / sizeof(float);
+  const size_t part_bytes = ws_bytes - 256 - colsum_ws_bytes(n, O);
 
   // dW[o,f] = sum_i dy[i,o] * a[i,f] : A(m=o,k=i) = dy[i*ld+o], B(n=f,k=i) = a[i*ld+f]
-  const float* as[2] = {a_l, a_r};
-  const int64_t lds[2] = {ld_al, ld_ar};
-  float* dws[2] = {dw_l, dw_r};
-  for (int w = 0; w < 2; ++w) {
-    if (!dws[w] || F == 0) continue;
-    int32_t rc = g_force_simt ? NGNN_E_UNSUPPORTED : tc_gemm_wgrad(dy, ld_dy, as[w], lds[w], n, F, O, dws[w], accumulate, part, st);
-    if (rc == NGNN_OK) continue;
-    if (rc != NGNN_E_UNSUPPORTED) return rc;
-    SimtGemmParams p{};
-    p.A1 = {dy, 1, ld_dy}; p.B1 = {as[w], 1, lds[w]}; p.K1 = n;
-    p.M = O; p.N = F; p.ldc = F;
-    if (S == 1 && !accumulate) {
-      p.C = dws[w]; p.split_stride = 0;
-      rc = launch_simt_gemm(p, 1, st);
-      if (rc != NGNN_OK) return rc;
-    } else {
-      p.C = part; p.split_stride = O * F;
-      rc = launch_simt_gemm(p, S, st);
-      if (rc != NGNN_OK) return rc;
-      k_reduce_partials<<<(unsigned)ceil_div(O * F, 256), 256, 0, st>>>(part, O * F, S, O * F, dws[w], accumulate);
-      NGNN_LAUNCH_CHECK();
+  bool done = false;
+  if (!g_force_simt && F > 0 && (dw_l || dw_r)) {
+    int32_t rc = tc_gemm_wgrad(dy, ld_dy, a_l, ld_al, a_r, ld_ar, n, F, O, dw_l, dw_r, accumulate, part, part_bytes, st);
+    if (rc == NGNN_OK) done = true;
+    else if (rc != NGNN_E_UNSUPPORTED) return rc;
+  }
+  if (!done) {
+    const int32_t S = wgrad_splits(n, F, O);
+    const float* as[2] = {a_l, a_r};
+    const int64_t lds[2] = {ld_al, ld_ar};
+    float* dws[2] = {dw_l, dw_r};
+    for (int w = 0; w < 2; ++w) {
+      if (!dws[w] || F == 0) continue;
+      SimtGemmParams p{};
+      p.A1 = {dy, 1, ld_dy}; p.B1 = {as[w], 1, lds[w]}; p.K1 = n;
+      p.M = O; p.N = F; p.ldc = F;
+      if (S == 1 && !accumulate) {
+        p.C = dws[w]; p.split_stride = 0;
+        int32_t rc = launch_simt_gemm(p, 1, st);
+        if (rc != NGNN_OK) return rc;
+      } else {
+        p.C = part; p.split_stride = O * F;
+        int32_t rc = launch_simt_gemm(p, S, st);
+        if (rc != NGNN_OK) return rc;
+        k_reduce_partials<<<(unsigned)ceil_div(O * F, 256), 256, 0, st>>>(part, O * F, S, O * F, dws[w], accumulate);
+        NGNN_LAUNCH_CHECK();
+      }
     }
   }
   if (db) {

@@ -354,7 +354,7 @@ static inline PFN_encodeTiled get_encode_fn() {
 
 // 2-D fp32 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 32 floats], SWIZZLE_128B
 static inline bool make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows,
-                                uint32_t box_cols = TC_BK) {
+                                uint32_t box_cols = TC_BK, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -362,7 +362,7 @@ static inline bool make_tmap_2d(CUtensorMap* map, const float* base, int64_t row
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -500,9 +500,251 @@ static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float*
   return tc_launch(tA, tA, tBh, tBl, p, pl, ns, st);
 }
 
-static inline int32_t tc_gemm_wgrad(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*,
-                                    int32_t, float*, cudaStream_t) {
-  return NGNN_E_UNSUPPORTED;
+// ----------------------------------------------------------------------------- K-WGRAD on tensor cores
+//   dW_seg[o, f] = sum_i dY[i, o] * X_seg[i, f]          (seg 0: X = mean -> dW_l, seg 1: X = root rows -> dW_r)
+// Both operands are MN-major for the UMMA (the reduction index i is the slow dimension of dY [n,O] and X [n,F]).
+// For 32-bit MN-major operands the only UMMA shared-memory layout is SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 128
+// bytes (32 MN elements) with the 32-byte chunks of a row XOR-ed by (row % 4) — what TMA writes for a
+// [32 rows(i) x 32 floats] box with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The 32-wide MN groups of a tile are
+// LBO = 4096 B (one box) apart, the 4-row k groups SBO = 512 B apart.  The long i dimension is split across CTAs (grid.z) into fixed
+// slices; each CTA writes its partial tile and k_reduce_partials sums them in a fixed order (deterministic).
+constexpr int TW_KB = 32;                      // reduction rows per K-block
+constexpr uint32_t TW_BOX_BYTES = TW_KB * 128; // one [32 x 32 floats] box
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                       // LayoutType::SWIZZLE_128B_BASE32B
+  return d;
+}
+
+struct TcWgradSeg {
+  float* out;                 // partials [splits][O][n_cols] (or the final dW when splits == 1)
+  int64_t split_stride;       // elements between split partials
+  int32_t n_cols;             // F
+  int32_t use_x2;             // 0: operand X1, 1: operand X2
+};
+struct TcWgradParams {
+  int32_t O;                  // rows of dW
+  int32_t BN;                 // UMMA N (multiple of 16)
+  int32_t nbox;               // ceil(BN / 32) boxes of X per K-block
+  int32_t stages;
+  int32_t tiles_per_seg;
+  int32_t kblocks_per_split;  // K-blocks (of 32 reduction rows) per grid.z slice
+  int32_t kblocks_total;
+  TcWgradSeg seg[2];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX1,
+           const __grid_constant__ CUtensorMap tmX2, const TcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const uint32_t a_bytes = 4 * TW_BOX_BYTES;                   // 128 o-columns: 16 KB
+  const uint32_t b_bytes = (uint32_t)p.nbox * TW_BOX_BYTES;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* full_conv = full_raw + TC_MAX_STAGES;
+  uint64_t* empty = full_conv + TC_MAX_STAGES;
+  uint64_t* tmem_full = empty + TC_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t o0 = blockIdx.x * TC_BM;
+  const int32_t seg_id = blockIdx.y / p.tiles_per_seg;
+  const int32_t n_tile = blockIdx.y - seg_id * p.tiles_per_seg;
+  const TcWgradSeg sg = p.seg[seg_id];
+  const int32_t f0 = n_tile * p.BN;
+  const int32_t kb_beg = blockIdx.z * p.kblocks_per_split;
+  const int32_t kb_end = min(p.kblocks_total, kb_beg + p.kblocks_per_split);
+  const int32_t KB = max(kb_end - kb_beg, 0);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmX2);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* tmX = sg.use_x2 ? &tmX2 : &tmX1;
+      for (int32_t it = 0; it < KB; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full_raw[s], a_bytes + b_bytes);
+        const int32_t i0 = (kb_beg + it) * TW_KB;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tma_load_2d(st + g * TW_BOX_BYTES, &tmDY, &full_raw[s], o0 + 32 * g, i0);
+        for (int g = 0; g < p.nbox; ++g) tma_load_2d(st + 2 * a_bytes + g * TW_BOX_BYTES, tmX, &full_raw[s], f0 + 32 * g, i0);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_tf32(TC_BM, (uint32_t)p.BN, 1, 1);   // both operands MN-major
+    for (int32_t it = 0; it < KB; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(&full_conv[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + 2 * a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+        for (int k = 0; k < TW_KB / 8; ++k) {
+          const uint32_t koff = k * 1024;   // 8 reduction rows x 128 B
+          const uint64_t dah = umma_desc_mn_sw128(a_hi + koff, TW_BOX_BYTES, 512), dal = umma_desc_mn_sw128(a_lo + koff, TW_BOX_BYTES, 512);
+          const uint64_t dbh = umma_desc_mn_sw128(b_hi + koff, TW_BOX_BYTES, 512), dbl = umma_desc_mn_sw128(b_lo + koff, TW_BOX_BYTES, 512);
+          umma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+        if (it == KB - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    const int n4 = (int)((a_bytes + b_bytes) / 16);            // float4s to split per stage (A then B, hi planes)
+    for (int32_t it = 0; it < KB; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(&full_raw[s], ph);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      const int a4 = (int)(a_bytes / 16);
+      for (int i = t; i < n4; i += 128) {
+        float4* hp; float4* lp;
+        if (i < a4) { hp = reinterpret_cast<float4*>(st) + i; lp = reinterpret_cast<float4*>(st + a_bytes) + i; }
+        else { hp = reinterpret_cast<float4*>(st + 2 * a_bytes) + (i - a4); lp = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes) + (i - a4); }
+        const float4 x = *hp;
+        float4 h, l;
+        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+        *hp = h;
+        *lp = l;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full_conv[s]);
+    }
+    // epilogue: partial tile -> global
+    const int q = warp & 3;
+    const int64_t o = (int64_t)o0 + q * 32 + lane;
+    float* orow = sg.out + (int64_t)blockIdx.z * sg.split_stride + o * sg.n_cols;
+    if (KB > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    for (int32_t c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      if (KB > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (o >= p.O) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int32_t f = f0 + c + j;
+        if (f < sg.n_cols) orow[f] = __uint_as_float(v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+struct TcWgradPlan {
+  int32_t BN, nbox, tiles_per_seg, stages, splits, kblocks_total, kblocks_per_split;
+  uint32_t smem_bytes;
+};
+static inline TcWgradPlan tc_wgrad_plan(int64_t n, int64_t F, int64_t O, int num_segs) {
+  TcWgradPlan pl;
+  pl.BN = F >= 256 ? 256 : round_up_i(F, 16);
+  pl.nbox = (pl.BN + 31) / 32;
+  pl.tiles_per_seg = (int32_t)ceil_div(F, pl.BN);
+  const uint32_t stage = 2u * 4u * TW_BOX_BYTES + 2u * (uint32_t)pl.nbox * TW_BOX_BYTES;
+  int st = (int)((TC_SMEM_LIMIT - 2048u) / stage);
+  pl.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+  pl.smem_bytes = (uint32_t)pl.stages * stage + 1024u + 256u;
+  pl.kblocks_total = (int32_t)ceil_div(n, TW_KB);
+  const int64_t tiles = ceil_div(O, TC_BM) * pl.tiles_per_seg * num_segs;
+  int64_t s = kNumSMs / tiles;                                   // one wave of CTAs (1 CTA / SM: smem-bound)
+  const int64_t max_s = ceil_div(pl.kblocks_total, 4);           // at least 4 K-blocks per slice
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  pl.kblocks_per_split = (int32_t)ceil_div(pl.kblocks_total, s);
+  pl.splits = (int32_t)ceil_div(pl.kblocks_total, pl.kblocks_per_split);
+  return pl;
+}
+// partial planes for both segments
+static inline size_t tc_wgrad_ws_bytes(int64_t n, int64_t F, int64_t O) {
+  const TcWgradPlan pl = tc_wgrad_plan(n, F, O, 2);
+  return 2 * align_up((size_t)pl.splits * O * F * sizeof(float), 256) + 256;
+}
+
+// dw_l (+)= dy^T a_l ; dw_r (+)= dy^T a_r.  UNSUPPORTED when an operand is not TMA-addressable.
+static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r,
+                                    int64_t ld_ar, int64_t n, int64_t F, int64_t O, float* dw_l, float* dw_r,
+                                    int32_t accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n < 1 || F < 4 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+  if (!tma_addressable(dy, ld_dy)) return NGNN_E_UNSUPPORTED;
+  if (dw_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
+  if (dw_r && !tma_addressable(a_r, ld_ar)) return NGNN_E_UNSUPPORTED;
+  if (!dw_l && !dw_r) return NGNN_OK;
+  if (ws == nullptr || ws_bytes < tc_wgrad_ws_bytes(n, F, O) || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
+  const int num_segs = (dw_l ? 1 : 0) + (dw_r ? 1 : 0);
+  const TcWgradPlan pl = tc_wgrad_plan(n, F, O, num_segs);
+
+  CUtensorMap tDY, tX1, tX2;
+  const float* x1 = dw_l ? a_l : a_r;
+  const int64_t ldx1 = dw_l ? ld_al : ld_ar;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  bool ok = make_tmap_2d(&tDY, dy, n, O, ld_dy, TW_KB, 32, sw);
+  ok = ok && make_tmap_2d(&tX1, x1, n, F, ldx1, TW_KB, 32, sw);
+  ok = ok && make_tmap_2d(&tX2, dw_r ? a_r : x1, n, F, dw_r ? ld_ar : ldx1, TW_KB, 32, sw);
+  NGNN_REQUIRE(ok, NGNN_E_CUDA, "wgrad: cuTensorMapEncodeTiled failed");
+
+  float* part0 = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  float* part1 = part0 + align_up((size_t)pl.splits * O * F * sizeof(float), 256) / sizeof(float);
+  const bool direct = pl.splits == 1 && !accumulate;
+  TcWgradParams p{};
+  p.O = (int32_t)O; p.BN = pl.BN; p.nbox = pl.nbox; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
+  p.kblocks_per_split = pl.kblocks_per_split; p.kblocks_total = pl.kblocks_total;
+  int ns = 0;
+  float* outs[2] = {nullptr, nullptr};
+  float* parts[2] = {nullptr, nullptr};
+  if (dw_l) { p.seg[ns] = TcWgradSeg{direct ? dw_l : part0, O * F, (int32_t)F, 0}; outs[ns] = dw_l; parts[ns] = part0; ++ns; }
+  if (dw_r) { p.seg[ns] = TcWgradSeg{direct ? dw_r : part1, O * F, (int32_t)F, dw_l ? 1 : 0}; outs[ns] = dw_r; parts[ns] = part1; ++ns; }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    NGNN_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(O, TC_BM), (unsigned)(pl.tiles_per_seg * ns), (unsigned)pl.splits);
+  k_tc_wgrad<<<grid, TC_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
+  NGNN_LAUNCH_CHECK();
+  if (!direct) {
+    for (int s = 0; s < ns; ++s) {
+      k_reduce_partials<<<(unsigned)ceil_div(O * F, 256), 256, 0, st>>>(parts[s], O * F, pl.splits, O * F, outs[s], accumulate);
+      NGNN_LAUNCH_CHECK();
+    }
+  }
+  return NGNN_OK;
 }
 
 }  // namespace ngnn
