@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the bounded cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--ncu-range", action="store_true", help="cudaProfilerStart/Stop around the first timed region")
+    ap.add_argument("--autograd", action="store_true", help="time the per-kernel autograd variant instead of the fused step")
     return ap.parse_args()
 
 
@@ -134,11 +135,9 @@ def run_ours(args):
     setup_s = time.time() - t_setup
 
     K, W = args.steps, args.warmup
-    order = loader.epoch_permutation(0)
     nb = loader.num_batches_global
-    host_seeds = [loader.batch_seeds(order, (i * world + rank) % nb).pin_memory() for i in range(K + W)]
-    dev_seeds = [s.to(device) for s in host_seeds]
-    bidx = [(i * world + rank) % nb for i in range(K + W)]
+    if W + K > len(loader):
+        raise SystemExit(f"--steps + --warmup = {W + K} exceeds one epoch ({len(loader)} steps per rank)")
 
     def barrier():
         if world > 1:
@@ -159,16 +158,21 @@ def run_ours(args):
             return float(t)
         return float(v)
 
-    # ---- warm-up (both loops share it: same kernels) ----
-    for i in range(W):
-        trainer.train_step(loader.sample(dev_seeds[i], epoch=0, batch_idx=bidx[i]))
-    trainer.reset_stats()
+    step_fn = trainer.train_step_autograd if args.autograd else trainer.train_step
 
-    # ---- timed region 1: `value` — inputs resident in HBM ----
+    # ---- timed region 1: `value` — every input (graph, features, labels, the epoch's seed order) resident in HBM ----
+    loader.seeds_on_device = True
+    loader.epoch = 0
+    it = iter(loader)
+    for _ in range(W):
+        step_fn(next(it))
+    trainer.reset_stats()
     agg_events, touched, ext = [], [], []
     ops.timers = {"agg_l1": agg_events}
     clocks = ClockSampler(local_rank)
     barrier()
+    if not args.autograd:
+        _lib.call("ngnn_probe_enable", K)
     if args.ncu_range:
         torch.cuda.profiler.start()
     launches0 = lib.ngnn_launch_count()
@@ -176,9 +180,9 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     edges = 0
-    for i in range(W, W + K):
-        batch = loader.sample(dev_seeds[i], epoch=0, batch_idx=bidx[i])
-        trainer.train_step(batch)
+    for _ in range(K):
+        batch = next(it)
+        step_fn(batch)
         edges += batch.num_edges
         n_dst, e1, _ = SAGE.layer_extents(batch.block, sh.layers)[0]
         ext.append((n_dst, e1))
@@ -191,19 +195,28 @@ def run_ours(args):
     clock_info = clocks.stop()
     launches = lib.ngnn_launch_count() - launches0
     ops.timers = None
+    del it
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     edges_total = sum_over_ranks(edges)
     value = edges_total / (ms_total * 1e-3)
 
-    # ---- roofline of the layer-1 aggregation (events recorded inside the timed region above) ----
-    agg_ms = [a.elapsed_time(b) for a, b in agg_events]
-    agg_bytes = [agg_l1_bytes(t, n_dst, e1, sh.features) for t, (n_dst, e1) in zip(touched, ext)]
+    # ---- roofline of the layer-1 aggregation: CUDA events recorded by the library around that launch, inside the
+    #      timed region above (ngnn_probe_*), or by ops._timed in the autograd variant
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    if args.autograd:
+        agg_ms = [a.elapsed_time(b) for a, b in agg_events]
+    else:
+        import ctypes
+        buf, cnt = (ctypes.c_float * K)(), ctypes.c_int32(0)
+        _lib.call("ngnn_probe_read", buf, K, ctypes.byref(cnt))
+        agg_ms = list(buf[:cnt.value])
+        _lib.call("ngnn_probe_enable", 0)
+    agg_bytes = [agg_l1_bytes(t, n_dst, e1, sh.features) for t, (n_dst, e1) in zip(touched, ext)]
     achieved = (sum(agg_bytes) / len(agg_bytes)) / (sum(agg_ms) / len(agg_ms) * 1e-3) / 1e9 if agg_ms else None
     roofline = {"kernel": "k_seg_reduce_v4 (K-AGG layer 1: mean of sampled in-neighbours + root gather from the resident table)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -211,45 +224,59 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "avg_launch_us": 1e3 * sum(agg_ms) / len(agg_ms) if agg_ms else None,
                 "algorithmic_bytes_per_launch": sum(agg_bytes) / len(agg_bytes) if agg_bytes else None,
-                "share_of_step": (sum(agg_ms) / ms_total) if agg_ms else None}
+                "share_of_step": (sum(agg_ms) / ms_total) if agg_ms else None,
+                "timing": "CUDA events on the launching stream around this kernel's launch, every step of the timed region"}
     del touched
 
-    # ---- timed region 2: `e2e` — through the public API with host seeds, loss/accuracy read back every step ----
+    # ---- timed region 2: `e2e` — public API with HOST seed buffers; loss / accuracy read back every step ----
+    loader.seeds_on_device = False
+    loader.epoch = 0
+    it = iter(loader)
+    for _ in range(W):
+        step_fn(next(it))
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     edges2 = 0
     t_wall = time.perf_counter()
-    for i in range(W, W + K):
-        batch = loader.sample(host_seeds[i], epoch=0, batch_idx=bidx[i])       # pinned H2D of the seed ids
-        trainer.train_step(batch)
-        loss, correct = trainer.read_stats()                                   # D2H (as float(loss)/int(correct), pipeline.py:164-165)
+    for _ in range(K):
+        batch = next(it)                                   # pinned H2D of the seed ids (inside the iterator)
+        step_fn(batch)
+        loss, correct = trainer.read_stats()               # D2H (float(loss)/int(correct) of reference pipeline.py:164-165)
         edges2 += batch.num_edges
-    e1.record()
+    e1_.record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    del it
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1_), wall_ms))
     e2e_value = sum_over_ranks(edges2) / (e2e_ms * 1e-3)
     H = len(sh.fanouts)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sh.batch_size * 8,
            "d2h_bytes_per_step": 8 + 4 * 2 * (H + 1), "ms_per_step": e2e_ms / K,
            "note": "graph + feature table uploaded once (resident); per step: seed ids H2D, block extents + loss/correct D2H"}
 
-    # ---- per-kernel-class breakdown (untimed extra pass, CUDA events around each ABI call) ----
+    # ---- per-kernel-class breakdown (untimed extra pass through the autograd variant: one FFI call per kernel class) ----
     breakdown = None
     if not args.no_breakdown and rank == 0:
+        loader.epoch = 0
+        it = iter(loader)
+        for _ in range(W):
+            trainer.train_step_autograd(next(it))
         ops.timers, ops.timers_open = {}, True
-        for i in range(W, min(W + 10, W + K)):
-            trainer.train_step(loader.sample(dev_seeds[i], epoch=0, batch_idx=bidx[i]))
+        nbk = min(10, K)
+        for _ in range(nbk):
+            trainer.train_step_autograd(next(it))
         torch.cuda.synchronize()
-        breakdown = {k: round(1e3 * sum(a.elapsed_time(b) for a, b in v) / max(1, min(10, K)), 2)
+        breakdown = {k: round(1e3 * sum(a.elapsed_time(b) for a, b in v) / nbk, 2)
                      for k, v in sorted(ops.timers.items())}          # us per step
         ops.timers, ops.timers_open = None, False
+        del it
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and args.cpu_steps > 0:
-        cpu_baseline = run_cpu_steps(loader, data, sh, host_seeds[:args.cpu_steps + 1], warmup=1)
+        order = loader.epoch_permutation(0)
+        cpu_baseline = run_cpu_steps(loader, data, sh, [loader.batch_seeds(order, i) for i in range(args.cpu_steps + 1)], warmup=1)
 
     if rank == 0:
         steps_per_epoch = -(-nb // world)

@@ -143,12 +143,18 @@ int32_t ngnn_act_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_
                      float scale, float* dz, int64_t ld_dz, ngnn_stream_t stream);
 
 /* ---- loss (F.cross_entropy on the seed rows, reference src/pipeline.py:155-165) ----
- * Mean softmax cross-entropy over bs rows against `target`; one launch produces
+ * Mean softmax cross-entropy over bs rows against `target`; a warp-per-row launch plus a fixed-order reduce produce
  *   stats[0] += mean loss, stats[1] += #(argmax == y_true)  (y_true NULL => skipped)
  *   dlogits[i,c] = (softmax_ic - [c==target_i]) * grad_scale / bs                          */
 int32_t ngnn_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true,
                         int64_t bs, int64_t C, float grad_scale, float* stats /*[2]*/,
-                        float* dlogits, int64_t ld_d, ngnn_stream_t stream);
+                        float* dlogits, int64_t ld_d, float* row_scratch /*[2*bs]*/, ngnn_stream_t stream);
+
+/* Same, with the labels gathered by id: target[row_ids[i]], y_true[row_ids[i]] (row_ids = the block's n_id, so the
+ * loader does not have to materialise y[n_id] / yhn[n_id]).  row_ids NULL = identity.                          */
+int32_t ngnn_ce_fwd_bwd_gather(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true,
+                               const int32_t* row_ids, int64_t bs, int64_t C, float grad_scale, float* stats /*[2]*/,
+                               float* dlogits, int64_t ld_d, float* row_scratch /*[2*bs]*/, ngnn_stream_t stream);
 
 /* ---- optimizer (torch.optim.Adam(lr), reference src/models/model.py:67-69) ----
  * One fused pass over a flat parameter bucket; step_count is the 1-based step t held in a
@@ -186,6 +192,56 @@ int32_t ngnn_sample_block(const int32_t* colptr, const int32_t* row, int64_t N,
                           int32_t replace, uint64_t seed, uint32_t epoch, uint32_t batch_idx,
                           int32_t* n_id, int32_t* rowptr, int32_t* col, int32_t* col_global, int32_t* e_pos,
                           int32_t* counts, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* ---- the whole step behind one call (loop body of PipelineCO.train, reference src/pipeline.py:152-168) ----
+ * SAGE network of reference src/models/layers/sage.py:7-40: num_layers SAGEConv layers
+ * (in_dim -> hidden_dim -> ... -> out_dim), ReLU + dropout between layers.  Parameters and gradients live in flat
+ * fp32 buckets laid out per layer as [lin_l.weight (O*F) | lin_l.bias (O) | lin_r.weight (O*F)] — the order of
+ * torch's module.parameters() for the reference module, so state_dicts map one to one.                             */
+typedef struct {
+  int32_t num_layers;
+  int32_t in_dim, hidden_dim, out_dim;
+  float   dropout;      /* applied between layers when training != 0 */
+  int32_t training;
+} ngnn_sage_model_t;
+
+/* A sampled block as produced by ngnn_sample_block (device arrays) with its per-hop extents on the host. */
+typedef struct {
+  const int32_t* rowptr;      /* [n+1]  */
+  const int32_t* col;         /* [e] local source ids  */
+  const int32_t* col_global;  /* [e] global source ids */
+  const int32_t* n_id;        /* [n] global id of local node */
+  int32_t        num_hops;    /* H */
+  const int32_t* hop_nodes;   /* (host) [H+1] cumulative nodes, hop_nodes[0] = batch size */
+  const int32_t* hop_edges;   /* (host) [H+1] cumulative edges, hop_edges[0] = 0 */
+} ngnn_block_t;
+
+int64_t ngnn_sage_num_params(const ngnn_sage_model_t* model);
+/* Arena size for blocks up to the given cumulative worst-case extents (host arrays [H+1], e.g. from
+ * ngnn_sample_capacity per hop).                                                                      */
+size_t  ngnn_sage_step_workspace_bytes(const ngnn_sage_model_t* model, int32_t num_hops,
+                                       const int64_t* max_hop_nodes, const int64_t* max_hop_edges);
+/* Forward (+ loss + backward) of one block.  Layer l of L computes only the rows within L-l hops of the seeds
+ * (exact for the seed rows); layer 1 reads the resident feature table `table` by global id.
+ *   grads  != NULL : training step — gradients of the mean CE over the seed rows are WRITTEN (not accumulated) to
+ *                    `grads`; dropout is active iff model->training.  Requires target_global.
+ *   grads  == NULL : forward (+ loss when target_global != NULL) only.
+ *   target_global / label_global: int64 [N] label arrays indexed by GLOBAL node id (yhn / y of the reference);
+ *                    stats[0] += mean loss, stats[1] += #(argmax == label) (label_global NULL => skipped).
+ *   logits_out (optional): [bs, out_dim] seed-row logits.
+ * No host synchronisation, no allocation; scratch = (ws, ws_bytes) from ngnn_sage_step_workspace_bytes.          */
+int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                       const int64_t* max_hop_nodes, const int64_t* max_hop_edges,
+                       const float* table, int64_t ld_table,
+                       const int64_t* target_global, const int64_t* label_global,
+                       uint64_t drop_seed, uint64_t drop_offset, float* stats /*[2]*/,
+                       float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* In-situ kernel timing for the roofline report: after ngnn_probe_enable(k), the next k ngnn_sage_step calls record
+ * a CUDA-event pair on their stream around the layer-1 K-AGG launch; ngnn_probe_read waits for them and returns the
+ * per-launch durations in milliseconds.  ngnn_probe_enable(0) disables and frees the events.                         */
+int32_t ngnn_probe_enable(int32_t max_samples);
+int32_t ngnn_probe_read(float* ms /*(host)[cap]*/, int32_t cap, int32_t* n /*(host)*/);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,14 @@ SIGNATURES = {
     "ngnn_sage_wgrad": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P,
                                   c_int32, _P, c_size_t, _P]),
     "ngnn_act_bwd": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_float, _P, c_int64, _P]),
-    "ngnn_ce_fwd_bwd": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int64, c_float, _P, _P, c_int64, _P]),
+    "ngnn_ce_fwd_bwd": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int64, c_float, _P, _P, c_int64, _P, _P]),
+    "ngnn_ce_fwd_bwd_gather": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_float, _P, _P, c_int64, _P, _P]),
+    "ngnn_sage_num_params": (c_int64, [_P]),
+    "ngnn_sage_step_workspace_bytes": (c_size_t, [_P, c_int32, _P, _P]),
+    "ngnn_sage_step": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, c_uint64, c_uint64, _P, _P, c_int64, _P,
+                                 c_size_t, _P]),
+    "ngnn_probe_enable": (c_int32, [c_int32]),
+    "ngnn_probe_read": (c_int32, [_P, c_int32, _P]),
     "ngnn_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P,
                                  c_int32, _P]),
     "ngnn_sample_capacity": (c_int32, [c_int32, _P, c_int32, c_int64, _P, _P]),
@@ -47,6 +54,18 @@ SIGNATURES = {
     "ngnn_sample_block": (c_int32, [_P, _P, c_int64, _P, c_int32, _P, c_int32, c_int32, c_uint64, c_uint32, c_uint32,
                                     _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
 }
+
+
+
+class SageModel(ctypes.Structure):      # ngnn_sage_model_t
+    _fields_ = [("num_layers", c_int32), ("in_dim", c_int32), ("hidden_dim", c_int32), ("out_dim", c_int32),
+                ("dropout", c_float), ("training", c_int32)]
+
+
+class BlockDesc(ctypes.Structure):      # ngnn_block_t
+    _fields_ = [("rowptr", c_void_p), ("col", c_void_p), ("col_global", c_void_p), ("n_id", c_void_p),
+                ("num_hops", c_int32), ("hop_nodes", ctypes.POINTER(c_int32)), ("hop_edges", ctypes.POINTER(c_int32))]
+
 
 _lib = None
 

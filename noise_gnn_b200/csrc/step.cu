@@ -1,0 +1,225 @@
+// step.cu — the whole mini-batch step of the hot loop behind ONE C-ABI call.
+//
+// ngnn_sage_step = loop body of PipelineCO.train (reference src/pipeline.py:152-169) for the SAGE network
+// of reference src/models/layers/sage.py:30-40 on one sampled block:
+//     forward (per layer: K-AGG -> K-GEMM with fused bias/ReLU/dropout) -> softmax-CE + accuracy count on
+//     the seed rows -> backward (per layer: K-WGRAD straight into the flat gradient bucket, K-DGRAD,
+//     CSR transpose, K-AGG-T with the producing layer's ReLU/dropout gate folded in).
+// Every layer is trimmed to the rows its seed outputs depend on (prefixes of the block; exact — SURVEY §8
+// trimming note), layer 1 aggregates straight from the resident feature table by global ids.  The launches
+// are issued back to back from C++ on the caller's stream (no host synchronisation, no allocation: all
+// scratch comes from one caller-owned arena), so the step costs one FFI crossing instead of ~80 and can be
+// captured in a CUDA graph.  The optimizer (ngnn_adam_step) is a separate call so a data-parallel caller can
+// all-reduce the gradient bucket in between.
+#include "common.cuh"
+
+namespace ngnn {
+
+struct LayerPlan {
+  int64_t F, O;                 // in / out channels
+  int64_t n_dst, e_lim, n_src;  // trimmed extents of this step
+  int64_t n_dst_max, e_max, n_src_max;
+  size_t off_wl, off_b, off_wr; // element offsets into the flat parameter / gradient buckets
+  // arena regions (byte offsets)
+  size_t mean, root, out, dy, colptr_t, row_t, perm_t;
+};
+
+struct StepPlan {
+  int L;
+  LayerPlan layer[16];
+  size_t dmean, droot, gemm_ws, dgrad_ws, wgrad_ws, sort_ws, ce_rows, total;
+  size_t gemm_ws_bytes, dgrad_ws_bytes, wgrad_ws_bytes, sort_ws_bytes;
+  int64_t n_params;
+};
+
+static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_hop_nodes, const int64_t* max_hop_edges,
+                      const int32_t* hop_nodes, const int32_t* hop_edges, StepPlan& pl) {
+  const int L = m->num_layers;
+  if (L < 1 || L > 16 || H < 1 || m->in_dim < 1 || m->out_dim < 1 || (L > 1 && m->hidden_dim < 1)) return false;
+  pl.L = L;
+  size_t off = 0, poff = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes > 0 ? bytes : 4, 256); return r; };
+  size_t max_dx = 0, gws = 0, dws = 0, wws = 0, sws = 0;
+  for (int i = 0; i < L; ++i) {
+    LayerPlan& lp = pl.layer[i];
+    lp.F = i == 0 ? m->in_dim : m->hidden_dim;
+    lp.O = i == L - 1 ? m->out_dim : m->hidden_dim;
+    const int d = L - 1 - i;   // hops between this layer's outputs and the seeds
+    const int a = d < H ? d : H, b = d + 1 < H ? d + 1 : H;
+    lp.n_dst_max = max_hop_nodes[a]; lp.e_max = max_hop_edges[b]; lp.n_src_max = max_hop_nodes[b];
+    if (hop_nodes) { lp.n_dst = hop_nodes[a]; lp.e_lim = hop_edges[b]; lp.n_src = hop_nodes[b]; }
+    else { lp.n_dst = lp.n_dst_max; lp.e_lim = lp.e_max; lp.n_src = lp.n_src_max; }
+    if (lp.n_dst > lp.n_dst_max || lp.e_lim > lp.e_max || lp.n_src > lp.n_src_max) return false;
+    lp.off_wl = poff; poff += (size_t)lp.O * lp.F;
+    lp.off_b = poff; poff += (size_t)lp.O;
+    lp.off_wr = poff; poff += (size_t)lp.O * lp.F;
+    lp.mean = take((size_t)lp.n_dst_max * lp.F * 4);
+    lp.root = i == 0 ? take((size_t)lp.n_dst_max * lp.F * 4) : 0;
+    lp.out = take((size_t)lp.n_dst_max * lp.O * 4);
+    lp.dy = take((size_t)lp.n_dst_max * lp.O * 4);
+    if (i > 0) {
+      lp.colptr_t = take((size_t)(lp.n_src_max + 1) * 4);
+      lp.row_t = take((size_t)lp.e_max * 4);
+      lp.perm_t = take((size_t)lp.e_max * 4);
+      if ((size_t)lp.n_dst_max * lp.F * 4 > max_dx) max_dx = (size_t)lp.n_dst_max * lp.F * 4;
+      const size_t s = ngnn_csr_transpose_workspace_bytes(lp.e_max, lp.n_src_max);
+      if (s > sws) sws = s;
+      const size_t dg = ngnn_sage_dgrad_workspace_bytes(lp.F, lp.O);
+      if (dg > dws) dws = dg;
+    }
+    const size_t g = ngnn_sage_gemm_workspace_bytes(lp.F, lp.O);
+    if (g > gws) gws = g;
+    const size_t w = ngnn_sage_wgrad_workspace_bytes(lp.n_dst_max, lp.F, lp.O);
+    if (w > wws) wws = w;
+  }
+  pl.n_params = (int64_t)poff;
+  pl.dmean = take(max_dx); pl.droot = take(max_dx);
+  pl.gemm_ws = take(gws); pl.dgrad_ws = take(dws); pl.wgrad_ws = take(wws); pl.sort_ws = take(sws);
+  pl.gemm_ws_bytes = gws; pl.dgrad_ws_bytes = dws; pl.wgrad_ws_bytes = wws; pl.sort_ws_bytes = sws;
+  pl.ce_rows = take((size_t)max_hop_nodes[0] * 2 * 4);
+  pl.total = off + 256;
+  return true;
+}
+
+// Optional in-situ timing of the layer-1 aggregation launch inside ngnn_sage_step (bench.py's roofline):
+// CUDA events recorded on the caller's stream around that one launch, a pair per step.
+static cudaEvent_t* g_probe_ev = nullptr;
+static int g_probe_cap = 0, g_probe_n = 0;
+
+}  // namespace ngnn
+
+using namespace ngnn;
+
+extern "C" {
+
+int32_t ngnn_probe_enable(int32_t max_samples) {
+  for (int i = 0; i < 2 * g_probe_cap; ++i) cudaEventDestroy(g_probe_ev[i]);
+  delete[] g_probe_ev;
+  g_probe_ev = nullptr; g_probe_cap = 0; g_probe_n = 0;
+  if (max_samples <= 0) return NGNN_OK;
+  g_probe_ev = new cudaEvent_t[2 * (size_t)max_samples];
+  for (int i = 0; i < 2 * max_samples; ++i) NGNN_CUDA(cudaEventCreate(&g_probe_ev[i]));
+  g_probe_cap = max_samples;
+  return NGNN_OK;
+}
+
+int32_t ngnn_probe_read(float* ms, int32_t cap, int32_t* n) {
+  NGNN_REQUIRE(ms && n, NGNN_E_INVALID, "probe_read: null pointer");
+  const int m = g_probe_n < cap ? g_probe_n : cap;
+  for (int i = 0; i < m; ++i) {
+    NGNN_CUDA(cudaEventSynchronize(g_probe_ev[2 * i + 1]));
+    NGNN_CUDA(cudaEventElapsedTime(&ms[i], g_probe_ev[2 * i], g_probe_ev[2 * i + 1]));
+  }
+  *n = m;
+  return NGNN_OK;
+}
+
+int64_t ngnn_sage_num_params(const ngnn_sage_model_t* model) {
+  if (!model) return -1;
+  int64_t n = 0;
+  for (int i = 0; i < model->num_layers; ++i) {
+    const int64_t F = i == 0 ? model->in_dim : model->hidden_dim;
+    const int64_t O = i == model->num_layers - 1 ? model->out_dim : model->hidden_dim;
+    n += 2 * O * F + O;
+  }
+  return n;
+}
+
+size_t ngnn_sage_step_workspace_bytes(const ngnn_sage_model_t* model, int32_t num_hops, const int64_t* max_hop_nodes,
+                                      const int64_t* max_hop_edges) {
+  StepPlan pl;
+  if (!model || !max_hop_nodes || !max_hop_edges || !make_plan(model, num_hops, max_hop_nodes, max_hop_edges, nullptr, nullptr, pl))
+    return 0;
+  return pl.total;
+}
+
+int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                       const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
+                       const int64_t* target_global, const int64_t* label_global, uint64_t drop_seed, uint64_t drop_offset,
+                       float* stats, float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  NGNN_REQUIRE(model && params && block && table && stats && ws, NGNN_E_INVALID, "sage_step: null pointer");
+  NGNN_REQUIRE(block->rowptr && block->col && block->col_global && block->n_id && block->hop_nodes && block->hop_edges,
+               NGNN_E_INVALID, "sage_step: incomplete block");
+  NGNN_REQUIRE(model->dropout >= 0.f && model->dropout < 1.f, NGNN_E_INVALID, "sage_step: dropout outside [0,1)");
+  StepPlan pl;
+  NGNN_REQUIRE(make_plan(model, block->num_hops, max_hop_nodes, max_hop_edges, block->hop_nodes, block->hop_edges, pl),
+               NGNN_E_INVALID, "sage_step: bad model / block extents (block larger than the declared capacity?)");
+  NGNN_REQUIRE(ws_bytes >= pl.total, NGNN_E_WORKSPACE, "sage_step: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+  NGNN_REQUIRE(ld_table >= model->in_dim, NGNN_E_INVALID, "sage_step: ld_table < in_dim");
+  const bool train = grads != nullptr;
+  NGNN_REQUIRE(!train || target_global != nullptr, NGNN_E_INVALID, "sage_step: training needs targets");
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  auto F32 = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  auto I32 = [&](size_t off) { return reinterpret_cast<int32_t*>(base + off); };
+  const int L = pl.L;
+  const int64_t bs = block->hop_nodes[0];
+  const float p_drop = (train && model->training) ? model->dropout : 0.f;
+  int32_t rc;
+
+  // ---------------- forward ----------------
+  for (int i = 0; i < L; ++i) {
+    const LayerPlan& lp = pl.layer[i];
+    const float* root;
+    int64_t ld_root;
+    if (i == 0) {   // aggregate from the resident table by global ids; gather the root rows in the same launch
+      const bool probe = g_probe_n < g_probe_cap;
+      if (probe) cudaEventRecord(g_probe_ev[2 * g_probe_n], as_stream(stream));
+      rc = ngnn_sage_agg_fwd(block->rowptr, block->col_global, table, ld_table, lp.n_dst, lp.F, F32(lp.mean), lp.F, block->n_id,
+                             F32(lp.root), lp.F, stream);
+      if (probe) { cudaEventRecord(g_probe_ev[2 * g_probe_n + 1], as_stream(stream)); ++g_probe_n; }
+      root = F32(lp.root); ld_root = lp.F;
+    } else {
+      const LayerPlan& prev = pl.layer[i - 1];
+      rc = ngnn_sage_agg_fwd(block->rowptr, block->col, F32(prev.out), prev.O, lp.n_dst, lp.F, F32(lp.mean), lp.F, nullptr,
+                             nullptr, 0, stream);
+      root = F32(prev.out); ld_root = prev.O;
+    }
+    if (rc != NGNN_OK) return rc;
+    const bool last = i == L - 1;
+    rc = ngnn_sage_gemm_fwd(F32(lp.mean), lp.F, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
+                            lp.n_dst, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
+                            drop_offset + (uint64_t)i, F32(lp.out), lp.O, nullptr, base + pl.gemm_ws, pl.gemm_ws_bytes, stream);
+    if (rc != NGNN_OK) return rc;
+  }
+  const LayerPlan& top = pl.layer[L - 1];
+  if (logits_out) {
+    NGNN_REQUIRE(ld_logits >= top.O, NGNN_E_INVALID, "sage_step: ld_logits < out_dim");
+    NGNN_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)ld_logits * 4, F32(top.out), (size_t)top.O * 4, (size_t)top.O * 4, (size_t)bs,
+                                cudaMemcpyDeviceToDevice, as_stream(stream)));
+  }
+  if (target_global == nullptr) return NGNN_OK;   // inference: forward only
+
+  // ---------------- loss on the seed rows (labels gathered by global id) ----------------
+  rc = ngnn_ce_fwd_bwd_gather(F32(top.out), top.O, target_global, label_global, block->n_id, bs, top.O, 1.0f, stats,
+                              train ? F32(top.dy) : nullptr, top.O, F32(pl.ce_rows), stream);
+  if (rc != NGNN_OK) return rc;
+  if (!train) return NGNN_OK;
+
+  // ---------------- backward ----------------
+  for (int i = L - 1; i >= 0; --i) {
+    const LayerPlan& lp = pl.layer[i];
+    const float* root = i == 0 ? F32(lp.root) : F32(pl.layer[i - 1].out);
+    const int64_t ld_root = i == 0 ? lp.F : pl.layer[i - 1].O;
+    // only the first bs rows of the top layer carry a gradient
+    const int64_t n_rows = i == L - 1 ? bs : lp.n_dst;
+    rc = ngnn_sage_wgrad(F32(lp.dy), lp.O, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
+                         grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
+    if (rc != NGNN_OK) return rc;
+    if (i == 0) break;   // features are leaves: no data gradient for layer 1
+    const LayerPlan& prev = pl.layer[i - 1];
+    const int64_t e_lim = i == L - 1 ? block->hop_edges[1 < block->num_hops ? 1 : block->num_hops] : lp.e_lim;
+    rc = ngnn_sage_dgrad(F32(lp.dy), lp.O, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows, lp.F, lp.O,
+                         F32(pl.dmean), lp.F, F32(pl.droot), lp.F, base + pl.dgrad_ws, pl.dgrad_ws_bytes, stream);
+    if (rc != NGNN_OK) return rc;
+    rc = ngnn_csr_transpose(block->rowptr, block->col, n_rows, e_lim, lp.n_src, I32(lp.colptr_t), I32(lp.row_t), I32(lp.perm_t),
+                            base + pl.sort_ws, pl.sort_ws_bytes, stream);
+    if (rc != NGNN_OK) return rc;
+    // dY of the previous layer = gate(prev output) * (transpose-sum of dmean + droot on the root rows)
+    rc = ngnn_sage_agg_bwd(I32(lp.colptr_t), I32(lp.row_t), F32(pl.dmean), lp.F, lp.n_src, lp.F, F32(pl.droot), lp.F, n_rows,
+                           F32(prev.out), prev.O, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.O, stream);
+    if (rc != NGNN_OK) return rc;
+  }
+  return NGNN_OK;
+}
+
+}  // extern "C"

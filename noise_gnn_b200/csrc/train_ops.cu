@@ -19,58 +19,61 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Single CTA, 32 warps; warp w handles rows w, w+32, ...; partial sums are combined in a fixed
-// order, so the loss is bitwise reproducible.
-__global__ void __launch_bounds__(1024) k_ce_fwd_bwd(const float* __restrict__ logits, int64_t ld,
-                                                     const int64_t* __restrict__ target,
-                                                     const int64_t* __restrict__ y_true, int64_t bs, int64_t C,
-                                                     float grad_scale, float* __restrict__ stats,
-                                                     float* __restrict__ dlogits, int64_t ld_d) {
-  __shared__ float s_loss[32];
-  __shared__ float s_corr[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float inv_bs = 1.0f / (float)bs;
-  float loss_acc = 0.f, corr_acc = 0.f;
-  for (int64_t i = warp; i < bs; i += 32) {
-    const float* row = logits + i * ld;
-    float mx = -INFINITY;
-    int64_t arg = 0;
-    for (int64_t c = lane; c < C; c += 32) {
-      const float v = row[c];
-      if (v > mx) { mx = v; arg = c; }
-    }
-    // argmax with first-index tie-break (torch.argmax semantics on ties are first occurrence)
+// One warp per row: log-sum-exp, gradient row, per-row loss / correct flag into `rows` ([2*bs]).
+__global__ void __launch_bounds__(256) k_ce_rows(const float* __restrict__ logits, int64_t ld,
+                                                 const int64_t* __restrict__ target, const int64_t* __restrict__ y_true,
+                                                 const int32_t* __restrict__ row_ids, int64_t bs, int64_t C,
+                                                 float grad_scale, float* __restrict__ rows,
+                                                 float* __restrict__ dlogits, int64_t ld_d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (i >= bs) return;
+  const float* row = logits + i * ld;
+  float mx = -INFINITY;
+  int64_t arg = 0;
+  for (int64_t c = lane; c < C; c += 32) {
+    const float v = row[c];
+    if (v > mx) { mx = v; arg = c; }
+  }
+  // argmax with first-index tie-break (torch.argmax returns the first maximal index)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
-      const int64_t oarg = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
-    }
-    float se = 0.f;
-    for (int64_t c = lane; c < C; c += 32) se += expf(row[c] - mx);
-    se = warp_sum(se);
-    const float lse = mx + logf(se);
-    const int64_t tgt = target[i];
-    if (dlogits != nullptr) {
-      const float g = grad_scale * inv_bs;
-      for (int64_t c = lane; c < C; c += 32) {
-        const float pr = expf(row[c] - lse);
-        dlogits[i * ld_d + c] = (pr - (c == tgt ? 1.f : 0.f)) * g;
-      }
-    }
-    if (lane == 0) {
-      loss_acc += (lse - row[tgt]);
-      if (y_true != nullptr && arg == y_true[i]) corr_acc += 1.f;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int64_t oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+  }
+  float se = 0.f;
+  for (int64_t c = lane; c < C; c += 32) se += expf(row[c] - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  const int64_t li = row_ids != nullptr ? (int64_t)row_ids[i] : i;   // label index (global id when gathering)
+  const int64_t tgt = target[li];
+  if (dlogits != nullptr) {
+    const float g = grad_scale / (float)bs;
+    for (int64_t c = lane; c < C; c += 32) {
+      const float pr = expf(row[c] - lse);
+      dlogits[i * ld_d + c] = (pr - (c == tgt ? 1.f : 0.f)) * g;
     }
   }
-  if (lane == 0) { s_loss[warp] = loss_acc; s_corr[warp] = corr_acc; }
+  if (lane == 0) {
+    rows[i] = lse - row[tgt];
+    rows[bs + i] = (y_true != nullptr && arg == y_true[li]) ? 1.f : 0.f;
+  }
+}
+
+// Single CTA: fixed-order tree sum of the per-row values => bitwise reproducible loss.
+__global__ void __launch_bounds__(1024) k_ce_reduce(const float* __restrict__ rows, int64_t bs, float* __restrict__ stats) {
+  __shared__ float s_l[1024];
+  __shared__ float s_c[1024];
+  float l = 0.f, c = 0.f;
+  for (int64_t i = threadIdx.x; i < bs; i += 1024) { l += rows[i]; c += rows[bs + i]; }
+  s_l[threadIdx.x] = l; s_c[threadIdx.x] = c;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float l = 0.f, c = 0.f;
-    for (int w = 0; w < 32; ++w) { l += s_loss[w]; c += s_corr[w]; }
-    stats[0] += l * inv_bs;
-    stats[1] += c;
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { s_l[threadIdx.x] += s_l[threadIdx.x + o]; s_c[threadIdx.x] += s_c[threadIdx.x + o]; }
+    __syncthreads();
   }
+  if (threadIdx.x == 0) { stats[0] += s_l[0] / (float)bs; stats[1] += s_c[0]; }
 }
 
 __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
@@ -100,16 +103,25 @@ using namespace ngnn;
 
 extern "C" {
 
-int32_t ngnn_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true, int64_t bs,
-                        int64_t C, float grad_scale, float* stats, float* dlogits, int64_t ld_d,
-                        ngnn_stream_t stream) {
+int32_t ngnn_ce_fwd_bwd_gather(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true,
+                               const int32_t* row_ids, int64_t bs, int64_t C, float grad_scale, float* stats, float* dlogits,
+                               int64_t ld_d, float* row_scratch, ngnn_stream_t stream) {
   NGNN_REQUIRE(bs >= 0 && C >= 0, NGNN_E_INVALID, "ce: negative size");
   if (bs == 0 || C == 0) return NGNN_OK;
-  NGNN_REQUIRE(logits && target && stats, NGNN_E_INVALID, "ce: null pointer");
+  NGNN_REQUIRE(logits && target && stats && row_scratch, NGNN_E_INVALID, "ce: null pointer");
   NGNN_REQUIRE(ld >= C && (dlogits == nullptr || ld_d >= C), NGNN_E_INVALID, "ce: leading dimension < C");
-  k_ce_fwd_bwd<<<1, 1024, 0, as_stream(stream)>>>(logits, ld, target, y_true, bs, C, grad_scale, stats, dlogits, ld_d);
+  k_ce_rows<<<(unsigned)ceil_div(bs * 32, 256), 256, 0, as_stream(stream)>>>(logits, ld, target, y_true, row_ids, bs, C,
+                                                                               grad_scale, row_scratch, dlogits, ld_d);
+  NGNN_LAUNCH_CHECK();
+  k_ce_reduce<<<1, 1024, 0, as_stream(stream)>>>(row_scratch, bs, stats);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;
+}
+
+int32_t ngnn_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true, int64_t bs,
+                        int64_t C, float grad_scale, float* stats, float* dlogits, int64_t ld_d, float* row_scratch,
+                        ngnn_stream_t stream) {
+  return ngnn_ce_fwd_bwd_gather(logits, ld, target, y_true, nullptr, bs, C, grad_scale, stats, dlogits, ld_d, row_scratch, stream);
 }
 
 int32_t ngnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

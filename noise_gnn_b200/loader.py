@@ -134,7 +134,7 @@ class NeighborLoader:
     def __init__(self, data, num_neighbors: Sequence[int], input_nodes=None, batch_size: int = 1,
                  shuffle: bool = False, replace: bool = False, num_workers: int = 0,
                  persistent_workers: bool = False, drop_last: bool = False, device=None, seed: int = 1232,
-                 rank: int = 0, world_size: int = 1, return_e_id: bool = False, **kwargs):
+                 rank: int = 0, world_size: int = 1, return_e_id: bool = False, seeds_on_device: bool = False, **kwargs):
         unsupported = {k: v for k, v in kwargs.items() if k in ("disjoint", "temporal_strategy", "time_attr",
                        "weight_attr", "subgraph_type", "transform", "filter_per_worker") and v not in (None, False, "directional")}
         if unsupported:
@@ -149,6 +149,7 @@ class NeighborLoader:
         self.batch_size, self.shuffle, self.replace, self.drop_last = int(batch_size), bool(shuffle), bool(replace), bool(drop_last)
         self.seed, self.rank, self.world_size = int(seed), int(rank), int(world_size)
         self.return_e_id = return_e_id
+        self.seeds_on_device = bool(seeds_on_device)   # keep each epoch's seed order in HBM (no per-step H2D at all)
         self.epoch = 0
         self.data = data
         N = data.num_nodes
@@ -213,41 +214,92 @@ class NeighborLoader:
         b = global_batch_idx % max(self.num_batches_global, 1)      # wrap-around pads the last DP round
         return order[b * self.batch_size:(b + 1) * self.batch_size]
 
-    def sample(self, seeds: torch.Tensor, epoch: int = 0, batch_idx: int = 0) -> Batch:
-        """Sample one block for explicit seeds (host or device int64)."""
+    def label_array(self, name: str) -> torch.Tensor:
+        """A node attribute as a contiguous int64 [N] device array indexed by global id (for the fused step)."""
+        cache = self.__dict__.setdefault("_label_cache", {})
+        src = self.node_attrs[name]
+        hit = cache.get(name)
+        if hit is None or hit[0] is not src:
+            cache[name] = (src, src.view(-1).to(torch.int64).contiguous())
+        return cache[name][1]
+
+    # ------------------------------------------------------------------ sampling
+    def _launch_sample(self, seeds: torch.Tensor, epoch: int, batch_idx: int):
+        """Enqueue one ngnn_sample_block on the CURRENT stream; returns the pending pieces (no host sync)."""
         H = len(self.num_neighbors)
-        with torch.cuda.device(self.device):
-            if not seeds.is_cuda:
-                seeds = seeds.pin_memory().to(self.device, non_blocking=True) if seeds.numel() else seeds.to(self.device)
-            seeds = seeds.to(torch.int64).contiguous()
-            bs = seeds.numel()
-            if bs == 0:
-                raise ValueError("cannot sample an empty seed batch")
-            if bs > self.batch_size:
-                raise ValueError(f"{bs} seeds exceed the loader's batch_size {self.batch_size}")
-            dev = self.device
-            n_id = torch.empty(self.max_nodes, dtype=torch.int32, device=dev)
-            rowptr = torch.empty(self.max_nodes + 1, dtype=torch.int32, device=dev)
-            col = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
-            colg = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
-            epos = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev) if self.return_e_id else None
-            counts = torch.empty(2 * (H + 1), dtype=torch.int32, device=dev)
-            with ops._timed("sample"):
-              _lib.call("ngnn_sample_block", ops._ptr(self.colptr), ops._ptr(self.row), self.num_nodes, ops._ptr(seeds), bs,
+        if not seeds.is_cuda:
+            seeds = (seeds if seeds.is_pinned() else seeds.pin_memory()).to(self.device, non_blocking=True)
+        seeds = seeds.to(torch.int64).contiguous()
+        bs = seeds.numel()
+        if bs == 0:
+            raise ValueError("cannot sample an empty seed batch")
+        if bs > self.batch_size:
+            raise ValueError(f"{bs} seeds exceed the loader's batch_size {self.batch_size}")
+        dev = self.device
+        n_id = torch.empty(self.max_nodes, dtype=torch.int32, device=dev)
+        rowptr = torch.empty(self.max_nodes + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
+        colg = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
+        epos = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev) if self.return_e_id else None
+        counts = torch.empty(2 * (H + 1), dtype=torch.int32, device=dev)
+        with ops._timed("sample"):
+            _lib.call("ngnn_sample_block", ops._ptr(self.colptr), ops._ptr(self.row), self.num_nodes, ops._ptr(seeds), bs,
                       self._fan, H, int(self.replace), self.seed & (2**64 - 1), epoch & 0xFFFFFFFF, batch_idx & 0xFFFFFFFF,
                       ops._ptr(n_id), ops._ptr(rowptr), ops._ptr(col), ops._ptr(colg), ops._ptr(epos), ops._ptr(counts),
                       ops._ptr(self._ws), self._ws.numel(), ops._stream())
-            c = counts.cpu().tolist()                      # the one host read per batch: block extents
-            hop_nodes, hop_edges = c[:H + 1], c[H + 1:]
-            n, e = hop_nodes[-1], hop_edges[-1]
-            block = ops.Block(rowptr[:n + 1], col[:e], n, e, hop_nodes=hop_nodes, hop_edges=hop_edges,
-                              col_global=colg[:e], n_id=n_id[:n])
-            return Batch(self, block, n_id[:n], None if epos is None else epos[:e], bs, seeds)
+        host_counts = torch.empty(2 * (H + 1), dtype=torch.int32, pin_memory=True)
+        host_counts.copy_(counts, non_blocking=True)      # the one device->host read per batch: block extents
+        return dict(seeds=seeds, bs=bs, n_id=n_id, rowptr=rowptr, col=col, colg=colg, epos=epos, counts=counts,
+                    host_counts=host_counts)
+
+    def _finish_sample(self, pend) -> Batch:
+        H = len(self.num_neighbors)
+        c = pend["host_counts"].tolist()
+        hop_nodes, hop_edges = c[:H + 1], c[H + 1:]
+        n, e = hop_nodes[-1], hop_edges[-1]
+        block = ops.Block(pend["rowptr"][:n + 1], pend["col"][:e], n, e, hop_nodes=hop_nodes, hop_edges=hop_edges,
+                          col_global=pend["colg"][:e], n_id=pend["n_id"][:n])
+        epos = pend["epos"]
+        return Batch(self, block, pend["n_id"][:n], None if epos is None else epos[:e], pend["bs"], pend["seeds"])
+
+    def sample(self, seeds: torch.Tensor, epoch: int = 0, batch_idx: int = 0) -> Batch:
+        """Sample one block for explicit seeds (host or device int64) on the current stream."""
+        with torch.cuda.device(self.device):
+            pend = self._launch_sample(seeds, epoch, batch_idx)
+            torch.cuda.current_stream().synchronize()
+            return self._finish_sample(pend)
 
     def __iter__(self):
+        """Yields device-resident batches; block i+1 is sampled on a side stream while the caller trains on block i."""
         epoch = self.epoch
         self.epoch += 1
         order = self.epoch_permutation(epoch)
-        for i in range(len(self)):
-            g = i * self.world_size + self.rank
-            yield self.sample(self.batch_seeds(order, g), epoch=epoch, batch_idx=g % max(self.num_batches_global, 1))
+        nb = max(self.num_batches_global, 1)
+        steps = len(self)
+        with torch.cuda.device(self.device):
+            if self.__dict__.get("_side") is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+
+            side.wait_stream(torch.cuda.current_stream())          # the resident graph was built on the caller's stream
+            order = order.to(self.device) if self.seeds_on_device else order.pin_memory()
+
+            def launch(i):
+                g = i * self.world_size + self.rank
+                with torch.cuda.stream(side):
+                    pend = self._launch_sample(self.batch_seeds(order, g), epoch, g % nb)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                return pend, ev
+
+            pending = launch(0) if steps > 0 else None
+            for i in range(steps):
+                pend, ev = pending
+                ev.synchronize()                                   # host needs the block extents of batch i
+                pending = launch(i + 1) if i + 1 < steps else None
+                main = torch.cuda.current_stream()
+                main.wait_event(ev)
+                for k in ("seeds", "n_id", "rowptr", "col", "colg", "epos", "counts"):
+                    if pend[k] is not None:
+                        pend[k].record_stream(main)                # allocated on the side stream, consumed on main
+                yield self._finish_sample(pend)

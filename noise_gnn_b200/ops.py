@@ -288,9 +288,10 @@ def ce_fwd_bwd(logits, target, y_true=None, grad_scale: float = 1.0, stats=None,
     if stats is None:
         stats = torch.zeros(2, dtype=_F32, device=logits.device)
     dlogits = torch.empty((bs, C), dtype=_F32, device=logits.device) if want_grad else None
+    scratch = torch.empty(2 * bs, dtype=_F32, device=logits.device)
     with _timed("ce"):
         _lib.call("ngnn_ce_fwd_bwd", _ptr(logits), _ld(logits), _ptr(target), _ptr(y_true), bs, C, float(grad_scale),
-                  _ptr(stats), _ptr(dlogits), _ld(dlogits) if dlogits is not None else 0, _stream())
+                  _ptr(stats), _ptr(dlogits), _ld(dlogits) if dlogits is not None else 0, _ptr(scratch), _stream())
     return stats, dlogits
 
 

@@ -36,7 +36,8 @@ class _SAGELayerFunction(torch.autograd.Function):
     post-activation output gates the backward (h > 0 <=> pre-activation > 0 and kept)."""
 
     @staticmethod
-    def forward(ctx, x_src, w_l, b_l, w_r, block, n_dst, e_limit, n_src, table_mode, act, drop_p, seed, offset, tag):
+    def forward(ctx, x_src, w_l, b_l, w_r, block, n_dst, e_limit, n_src, table_mode, act, drop_p, seed, offset, tag,
+                in_gate_scale=0.0, grad_pregated=False):
         if table_mode:   # aggregate from the resident table by global ids, gather the root rows in the same launch
             mean, root = ops.agg_fwd(block.rowptr, block.col_global, x_src, n_dst, root_idx=block.n_id, tag="agg_" + tag)
         else:
@@ -46,13 +47,15 @@ class _SAGELayerFunction(torch.autograd.Function):
         ctx.save_for_backward(mean, root, w_l, w_r, out if act or drop_p > 0 else None)
         ctx.block, ctx.n_dst, ctx.e_limit, ctx.n_src = block, n_dst, e_limit, n_src
         ctx.table_mode, ctx.act, ctx.drop_p, ctx.tag = table_mode, act, drop_p, tag
+        ctx.in_gate_scale, ctx.grad_pregated = in_gate_scale, grad_pregated
         return out
 
     @staticmethod
     def backward(ctx, dy):
         mean, root, w_l, w_r, out = ctx.saved_tensors
+        x_src_saved = root   # in layer mode the root operand IS x_src (all n_src rows)
         block, n_dst = ctx.block, ctx.n_dst
-        if out is not None:
+        if out is not None and not ctx.grad_pregated:   # else the consumer layer already applied this layer's ReLU/dropout gate
             dy = ops.act_bwd(dy, out, 1.0 / (1.0 - ctx.drop_p))
         F_ = mean.size(1)
         dw_l, dw_r, db = ops.wgrad(dy, mean, root, n_dst, F_, tag="wgrad_" + ctx.tag)
@@ -60,8 +63,11 @@ class _SAGELayerFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0] and not ctx.table_mode:
             dmean, droot = ops.dgrad(dy, w_l, w_r, block.rowptr, n_dst, tag="dgrad_" + ctx.tag)
             colptr_t, row_t = block.transpose(ctx.e_limit, ctx.n_src)
-            dx = ops.agg_bwd(colptr_t, row_t, dmean, ctx.n_src, dx_root=droot, n_root=n_dst, tag="aggT_" + ctx.tag)
-        return (dx, dw_l, db, dw_r) + (None,) * 10
+            # x_src is the producing layer's post-activation output: fold its ReLU+dropout backward into this pass
+            gate = x_src_saved if ctx.in_gate_scale > 0 else None
+            dx = ops.agg_bwd(colptr_t, row_t, dmean, ctx.n_src, dx_root=droot, n_root=n_dst, act_ref=gate,
+                             act_scale=ctx.in_gate_scale, tag="aggT_" + ctx.tag)
+        return (dx, dw_l, db, dw_r) + (None,) * 12
 
 
 class SAGE(torch.nn.Module):
@@ -123,7 +129,9 @@ class SAGE(torch.nn.Module):
             act = NGNN_ACT_RELU if i != last else NGNN_ACT_NONE
             h = _SAGELayerFunction.apply(h, conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, block, n_dst, e_limit,
                                          n_src, i == 0, act, p if i != last else 0.0, self.drop_seed,
-                                         self._drop_calls * self.num_layers + i, f"l{i + 1}")
+                                         self._drop_calls * self.num_layers + i, f"l{i + 1}",
+                                         (1.0 / (1.0 - p)) if i > 0 else 0.0,   # input = previous layer's relu/dropout output
+                                         i != last)                              # the next layer gates this layer's gradient
         return h[: batch.batch_size]
 
     # ---- layer-wise inference (reference sage.py:42-58) -----------------------------------------

@@ -1,24 +1,29 @@
 """Train step of the hot loop — the body of ``PipelineCO.train`` (reference src/pipeline.py:152-169) on the
-B200-native path, host-sync-free after sampling:
+B200-native path:
 
-    batch -> SAGE.forward_batch (trimmed, fused) -> softmax-CE + accuracy count on the seed rows
-          -> backward -> [DP: one NCCL all-reduce of the flat gradient bucket] -> fused Adam.
+    batch -> ngnn_sage_step (ONE C-ABI call: trimmed fused SAGE forward, softmax-CE + accuracy count on the seed
+             rows, backward straight into the flat gradient bucket)
+          -> [DP: one NCCL all-reduce of the flat gradient bucket] -> ngnn_adam_step (fused Adam).
 
-Parameters, gradients and Adam state live in flat fp32 buckets (the model's ``Parameter``s are views into
-them, so ``state_dict`` keeps PyG's names); loss / accuracy accumulate in a device tensor and are read by
-the caller when it wants them (the reference reads them every step, src/pipeline.py:164-165).
+Parameters, gradients and Adam state live in flat fp32 buckets (the model's ``Parameter``s are views into them,
+so ``state_dict`` keeps PyG's names); loss / accuracy accumulate in a device tensor and are read by the caller
+when it wants them (the reference reads them every step, src/pipeline.py:164-165).  Nothing in the step
+synchronises with the host.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class FlatBuckets:
-    """Re-homes a module's parameters (and their .grad) into contiguous flat fp32 buffers."""
+    """Re-homes a module's parameters (and their .grad) into contiguous flat fp32 buffers, in
+    ``module.parameters()`` order — for SAGE: per layer lin_l.weight, lin_l.bias, lin_r.weight, which is
+    the layout ngnn_sage_step expects."""
 
     def __init__(self, module: torch.nn.Module):
         params = [p for p in module.parameters() if p.requires_grad]
@@ -51,8 +56,19 @@ class FlatBuckets:
             off += n
 
 
+def hop_capacities(batch_size: int, fanouts, num_nodes: int):
+    """Cumulative worst-case nodes / edges after each hop (the extents ngnn_sample_block can produce)."""
+    fr, nodes, edges = batch_size, [batch_size], [0]
+    for f in fanouts:
+        e = fr * f
+        edges.append(edges[-1] + e)
+        fr = min(e, num_nodes)
+        nodes.append(min(nodes[-1] + fr, num_nodes + batch_size))
+    return nodes, edges
+
+
 class Trainer:
-    """Owns the flat buckets and the fused optimizer for one SAGE network."""
+    """Owns the flat buckets, the step arena and the fused optimizer for one SAGE network."""
 
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  process_group=None, world_size: int = 1):
@@ -65,6 +81,16 @@ class Trainer:
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)     # [sum of step losses, #correct]
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.process_group, self.world_size = process_group, world_size
+        self.steps = 0
+        self._arena = None
+        self._arena_key = None
+        convs = model.convs
+        self._cfg = dict(num_layers=len(convs), in_dim=convs[0].in_channels,
+                         hidden_dim=convs[0].out_channels if len(convs) > 1 else convs[0].out_channels,
+                         out_dim=convs[-1].out_channels)
+        n_expected = sum(2 * c.in_channels * c.out_channels + c.out_channels for c in convs)
+        if n_expected != self.buckets.numel:
+            raise ValueError("the fused step expects a plain SAGE stack (lin_l.weight, lin_l.bias, lin_r.weight per layer)")
 
     def reset_stats(self):
         self.stats.zero_()
@@ -74,7 +100,67 @@ class Trainer:
         s = self.stats.tolist()
         return s[0], int(s[1])
 
-    def train_step(self, batch, target_attr: str = "yhn", label_attr: Optional[str] = "y"):
+    # ------------------------------------------------------------------ fused step
+    def _model_struct(self, training: bool):
+        m = self.model
+        return _lib.SageModel(self._cfg["num_layers"], self._cfg["in_dim"], self._cfg["hidden_dim"], self._cfg["out_dim"],
+                              float(m.dropout), int(training))
+
+    def _ensure_arena(self, loader, ms):
+        key = (loader.batch_size, tuple(loader.num_neighbors), loader.num_nodes)
+        if self._arena_key != key:
+            nodes, edges = hop_capacities(loader.batch_size, loader.num_neighbors, loader.num_nodes)
+            H = len(loader.num_neighbors)
+            self._max_nodes = (ctypes.c_int64 * (H + 1))(*nodes)
+            self._max_edges = (ctypes.c_int64 * (H + 1))(*edges)
+            nbytes = _lib.load().ngnn_sage_step_workspace_bytes(ctypes.byref(ms), H, self._max_nodes, self._max_edges)
+            if nbytes == 0:
+                raise RuntimeError("ngnn_sage_step_workspace_bytes rejected the model / loader configuration")
+            self._arena = torch.empty(nbytes, dtype=torch.uint8, device=self.buckets.param.device)
+            self._arena_key = key
+        return self._arena
+
+    def forward_backward(self, batch, target_attr: Optional[str] = "yhn", label_attr: Optional[str] = "y",
+                         train: bool = True, want_logits: bool = False):
+        """One ngnn_sage_step call on a Batch of our NeighborLoader; gradients land in the flat bucket."""
+        loader, blk = batch._loader, batch.block
+        ms = self._model_struct(training=train and self.model.training)
+        arena = self._ensure_arena(loader, ms)
+        H = len(blk.hop_nodes) - 1
+        hop_n = (ctypes.c_int32 * (H + 1))(*blk.hop_nodes)
+        hop_e = (ctypes.c_int32 * (H + 1))(*blk.hop_edges)
+        bd = _lib.BlockDesc(blk.rowptr.data_ptr(), blk.col.data_ptr(), blk.col_global.data_ptr(), blk.n_id.data_ptr(), H,
+                            hop_n, hop_e)
+        tgt = loader.label_array(target_attr) if target_attr else None
+        lab = loader.label_array(label_attr) if label_attr else None
+        logits = None
+        if want_logits:
+            logits = torch.empty((batch.batch_size, self._cfg["out_dim"]), dtype=torch.float32, device=arena.device)
+        self.steps += 1
+        with ops._timed("sage_step"):
+            _lib.call("ngnn_sage_step", ctypes.byref(ms), ops._ptr(self.buckets.param),
+                      ops._ptr(self.buckets.grad) if train else None, ctypes.byref(bd), self._max_nodes, self._max_edges,
+                      ops._ptr(loader.x), loader.x.stride(0), ops._ptr(tgt), ops._ptr(lab), self.model.drop_seed,
+                      self.steps * self._cfg["num_layers"], ops._ptr(self.stats), ops._ptr(logits),
+                      logits.stride(0) if logits is not None else 0, ops._ptr(arena), arena.numel(), ops._stream())
+        return logits
+
+    def optimizer_step(self):
+        bk = self.buckets
+        scale = 1.0
+        if self.world_size > 1:               # DP: one all-reduce of the flat bucket, then average
+            torch.distributed.all_reduce(bk.grad, group=self.process_group)
+            scale = 1.0 / self.world_size
+        ops.adam_step(bk.param, bk.grad, self.exp_avg, self.exp_avg_sq, self.step_dev, lr=self.lr, betas=self.betas,
+                      eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
+
+    def train_step(self, batch, target_attr: str = "yhn", label_attr: Optional[str] = "y", want_logits: bool = False):
+        logits = self.forward_backward(batch, target_attr, label_attr, train=True, want_logits=want_logits)
+        self.optimizer_step()
+        return logits
+
+    # ------------------------------------------------------------------ autograd variant (same kernels, ~80 FFI calls)
+    def train_step_autograd(self, batch, target_attr: str = "yhn", label_attr: Optional[str] = "y"):
         model, bk = self.model, self.buckets
         bs = batch.batch_size
         logits = model.forward_batch(batch)
@@ -84,10 +170,5 @@ class Trainer:
         bk.grad.zero_()                       # optimizer.zero_grad()
         logits.backward(dlogits)              # loss.backward(): wgrad / dgrad / transpose-sum kernels
         bk.rebind_grads()
-        scale = 1.0
-        if self.world_size > 1:               # DP: one all-reduce of the flat bucket, then average
-            torch.distributed.all_reduce(bk.grad, group=self.process_group)
-            scale = 1.0 / self.world_size
-        ops.adam_step(bk.param, bk.grad, self.exp_avg, self.exp_avg_sq, self.step_dev, lr=self.lr, betas=self.betas,
-                      eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
+        self.optimizer_step()
         return logits
