@@ -24,8 +24,8 @@ static int32_t wgrad_splits(int64_t n, int64_t F, int64_t O) {
   return (int32_t)s;
 }
 static int32_t colsum_slices(int64_t n) {
-  int64_t s = ceil_div(n, 256);
-  if (s > 512) s = 512;
+  int64_t s = ceil_div(n, 128);
+  if (s > 296) s = 296;            // ~2 CTAs per SM per 32-column strip
   if (s < 1) s = 1;
   return (int32_t)s;
 }
@@ -174,8 +174,8 @@ int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_
   if (db) {
     const int32_t Cs = colsum_slices(n);
     const int64_t rows = ceil_div(n, Cs);
-    dim3 grid((unsigned)ceil_div(O, 128), (unsigned)Cs);
-    k_colsum_partial<<<grid, 128, 0, st>>>(dy, ld_dy, n, O, rows, cpart);
+    dim3 grid((unsigned)ceil_div(O, 32), (unsigned)Cs);
+    k_colsum_partial<<<grid, 256, 0, st>>>(dy, ld_dy, n, O, rows, cpart);
     NGNN_LAUNCH_CHECK();
     k_reduce_partials<<<(unsigned)ceil_div(O, 256), 256, 0, st>>>(cpart, O, Cs, O, db, accumulate);
     NGNN_LAUNCH_CHECK();

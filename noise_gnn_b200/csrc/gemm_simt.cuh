@@ -161,16 +161,35 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int64_t stride
   out[i] = accumulate ? out[i] + s : s;
 }
 
-// column sums of dy over a row slice: part[z*O + o] = sum_{i in slice z} dy[i*ld + o]
-__global__ void k_colsum_partial(const float* __restrict__ dy, int64_t ld, int64_t n, int64_t O, int64_t rows_per_slice,
-                                 float* __restrict__ part) {
-  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (o >= O) return;
+// column sums of dy over a row slice: part[z*O + o] = sum_{i in slice z} dy[i*ld + o].
+// Block = 32 columns x 8 row lanes: every warp reads 128 contiguous bytes of a row; the 8 row lanes are combined
+// through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict__ dy, int64_t ld, int64_t n, int64_t O,
+                                                        int64_t rows_per_slice, float* __restrict__ part) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t o = (int64_t)blockIdx.x * 32 + tx;
   const int64_t i0 = (int64_t)blockIdx.y * rows_per_slice;
   const int64_t i1 = min(n, i0 + rows_per_slice);
-  float s = 0.f;
-  for (int64_t i = i0; i < i1; ++i) s += __ldg(dy + i * ld + o);
-  part[(int64_t)blockIdx.y * O + o] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (o < O) {
+    int64_t i = i0 + ty;
+    for (; i + 24 < i1; i += 32) {
+      s0 += __ldg(dy + i * ld + o);
+      s1 += __ldg(dy + (i + 8) * ld + o);
+      s2 += __ldg(dy + (i + 16) * ld + o);
+      s3 += __ldg(dy + (i + 24) * ld + o);
+    }
+    for (; i < i1; i += 8) s0 += __ldg(dy + i * ld + o);
+  }
+  sm[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && o < O) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += sm[r][tx];
+    part[(int64_t)blockIdx.y * O + o] = s;
+  }
 }
 
 __global__ void k_act_bwd(const float* __restrict__ dh, int64_t ld_dh, const float* __restrict__ h, int64_t ld_h,

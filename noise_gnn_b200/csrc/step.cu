@@ -17,6 +17,7 @@ namespace ngnn {
 
 struct LayerPlan {
   int64_t F, O;                 // in / out channels
+  int64_t ldo;                  // leading dimension of this layer's out / dy buffers (O rounded up to 4: TMA-addressable)
   int64_t n_dst, e_lim, n_src;  // trimmed extents of this step
   int64_t n_dst_max, e_max, n_src_max;
   size_t off_wl, off_b, off_wr; // element offsets into the flat parameter / gradient buckets
@@ -44,6 +45,7 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     LayerPlan& lp = pl.layer[i];
     lp.F = i == 0 ? m->in_dim : m->hidden_dim;
     lp.O = i == L - 1 ? m->out_dim : m->hidden_dim;
+    lp.ldo = (lp.O + 3) / 4 * 4;
     const int d = L - 1 - i;   // hops between this layer's outputs and the seeds
     const int a = d < H ? d : H, b = d + 1 < H ? d + 1 : H;
     lp.n_dst_max = max_hop_nodes[a]; lp.e_max = max_hop_edges[b]; lp.n_src_max = max_hop_nodes[b];
@@ -55,8 +57,8 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     lp.off_wr = poff; poff += (size_t)lp.O * lp.F;
     lp.mean = take((size_t)lp.n_dst_max * lp.F * 4);
     lp.root = i == 0 ? take((size_t)lp.n_dst_max * lp.F * 4) : 0;
-    lp.out = take((size_t)lp.n_dst_max * lp.O * 4);
-    lp.dy = take((size_t)lp.n_dst_max * lp.O * 4);
+    lp.out = take((size_t)lp.n_dst_max * lp.ldo * 4);
+    lp.dy = take((size_t)lp.n_dst_max * lp.ldo * 4);
     if (i > 0) {
       lp.colptr_t = take((size_t)(lp.n_src_max + 1) * 4);
       lp.row_t = take((size_t)lp.e_max * 4);
@@ -170,28 +172,28 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
       root = F32(lp.root); ld_root = lp.F;
     } else {
       const LayerPlan& prev = pl.layer[i - 1];
-      rc = ngnn_sage_agg_fwd(block->rowptr, block->col, F32(prev.out), prev.O, lp.n_dst, lp.F, F32(lp.mean), lp.F, nullptr,
+      rc = ngnn_sage_agg_fwd(block->rowptr, block->col, F32(prev.out), prev.ldo, lp.n_dst, lp.F, F32(lp.mean), lp.F, nullptr,
                              nullptr, 0, stream);
-      root = F32(prev.out); ld_root = prev.O;
+      root = F32(prev.out); ld_root = prev.ldo;
     }
     if (rc != NGNN_OK) return rc;
     const bool last = i == L - 1;
     rc = ngnn_sage_gemm_fwd(F32(lp.mean), lp.F, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
                             lp.n_dst, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
-                            drop_offset + (uint64_t)i, F32(lp.out), lp.O, nullptr, base + pl.gemm_ws, pl.gemm_ws_bytes, stream);
+                            drop_offset + (uint64_t)i, F32(lp.out), lp.ldo, nullptr, base + pl.gemm_ws, pl.gemm_ws_bytes, stream);
     if (rc != NGNN_OK) return rc;
   }
   const LayerPlan& top = pl.layer[L - 1];
   if (logits_out) {
     NGNN_REQUIRE(ld_logits >= top.O, NGNN_E_INVALID, "sage_step: ld_logits < out_dim");
-    NGNN_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)ld_logits * 4, F32(top.out), (size_t)top.O * 4, (size_t)top.O * 4, (size_t)bs,
+    NGNN_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)ld_logits * 4, F32(top.out), (size_t)top.ldo * 4, (size_t)top.O * 4, (size_t)bs,
                                 cudaMemcpyDeviceToDevice, as_stream(stream)));
   }
   if (target_global == nullptr) return NGNN_OK;   // inference: forward only
 
   // ---------------- loss on the seed rows (labels gathered by global id) ----------------
-  rc = ngnn_ce_fwd_bwd_gather(F32(top.out), top.O, target_global, label_global, block->n_id, bs, top.O, 1.0f, stats,
-                              train ? F32(top.dy) : nullptr, top.O, F32(pl.ce_rows), stream);
+  rc = ngnn_ce_fwd_bwd_gather(F32(top.out), top.ldo, target_global, label_global, block->n_id, bs, top.O, 1.0f, stats,
+                              train ? F32(top.dy) : nullptr, top.ldo, F32(pl.ce_rows), stream);
   if (rc != NGNN_OK) return rc;
   if (!train) return NGNN_OK;
 
@@ -199,16 +201,16 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
   for (int i = L - 1; i >= 0; --i) {
     const LayerPlan& lp = pl.layer[i];
     const float* root = i == 0 ? F32(lp.root) : F32(pl.layer[i - 1].out);
-    const int64_t ld_root = i == 0 ? lp.F : pl.layer[i - 1].O;
+    const int64_t ld_root = i == 0 ? lp.F : pl.layer[i - 1].ldo;
     // only the first bs rows of the top layer carry a gradient
     const int64_t n_rows = i == L - 1 ? bs : lp.n_dst;
-    rc = ngnn_sage_wgrad(F32(lp.dy), lp.O, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
+    rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
                          grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
     if (rc != NGNN_OK) return rc;
     if (i == 0) break;   // features are leaves: no data gradient for layer 1
     const LayerPlan& prev = pl.layer[i - 1];
     const int64_t e_lim = i == L - 1 ? block->hop_edges[1 < block->num_hops ? 1 : block->num_hops] : lp.e_lim;
-    rc = ngnn_sage_dgrad(F32(lp.dy), lp.O, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows, lp.F, lp.O,
+    rc = ngnn_sage_dgrad(F32(lp.dy), lp.ldo, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows, lp.F, lp.O,
                          F32(pl.dmean), lp.F, F32(pl.droot), lp.F, base + pl.dgrad_ws, pl.dgrad_ws_bytes, stream);
     if (rc != NGNN_OK) return rc;
     rc = ngnn_csr_transpose(block->rowptr, block->col, n_rows, e_lim, lp.n_src, I32(lp.colptr_t), I32(lp.row_t), I32(lp.perm_t),
@@ -216,7 +218,7 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
     if (rc != NGNN_OK) return rc;
     // dY of the previous layer = gate(prev output) * (transpose-sum of dmean + droot on the root rows)
     rc = ngnn_sage_agg_bwd(I32(lp.colptr_t), I32(lp.row_t), F32(pl.dmean), lp.F, lp.n_src, lp.F, F32(pl.droot), lp.F, n_rows,
-                           F32(prev.out), prev.O, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.O, stream);
+                           F32(prev.out), prev.ldo, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.ldo, stream);
     if (rc != NGNN_OK) return rc;
   }
   return NGNN_OK;

@@ -73,6 +73,10 @@ class _SAGELayerFunction(torch.autograd.Function):
 class SAGE(torch.nn.Module):
     def __init__(self, in_size, hidden_size, out_size, num_layers, dropout=0.5, use_bn=False):
         super().__init__()
+        if num_layers < 2:
+            # the reference constructor always appends a first and a last conv (sage.py:16-19), so num_layers=1 there
+            # means two convs with the activation after the LAST one — a quirk no reference config uses
+            raise NotImplementedError("SAGE needs num_layers >= 2 (every reference config uses 2 or 3)")
         self.num_layers, self.dropout, self.use_bn = num_layers, dropout, use_bn
         dims = [in_size] + [hidden_size] * (num_layers - 1) + [out_size]
         self.convs = torch.nn.ModuleList(SAGEConv(dims[i], dims[i + 1]) for i in range(num_layers))

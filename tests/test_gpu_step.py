@@ -30,7 +30,7 @@ def _setup(dev, L, fan, dropout, bs=64, hidden=64, name="arxiv", scale=0.02):
     return data, sh, loader, ref, net
 
 
-@pytest.mark.parametrize("L,fan", [(3, [15, 10, 5]), (3, [10, 5]), (2, [10, 5]), (1, [7]), (2, [4, 4, 4])])
+@pytest.mark.parametrize("L,fan", [(3, [15, 10, 5]), (3, [10, 5]), (2, [10, 5]), (2, [7]), (2, [4, 4, 4]), (4, [5, 5])])
 def test_fused_step_matches_oracle_and_autograd(dev, L, fan):
     from noise_gnn_b200.train import Trainer
     data, sh, loader, ref, net = _setup(dev, L, fan, dropout=0.0)
