@@ -87,6 +87,10 @@ int32_t ngnn_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const float
                           const int32_t* root_idx, float* root, int64_t ld_root,
                           ngnn_stream_t stream);
 
+/* Development knob for kernel sweeps (profiles/prof_agg.py): key 0 = neighbour rows in flight per lane for
+ * F <= 128 (2/4/8, 0 = default), key 1 = CTA size of the aggregation kernels (128/256/512).            */
+int32_t ngnn_set_tuning(int32_t key, int32_t value);
+
 /* ---- K-AGG-T: transpose (CSC) segment sum, backward of K-AGG ----
  *   dx[j,:] = gate_j * ( sum_{q in [colptr_t[j],colptr_t[j+1])} dmean_scaled[row_t[q],:]
  *                        + (j < n_root ? dx_root[j,:] : 0) )                         for j < n_src

@@ -25,6 +25,7 @@ SIGNATURES = {
     "ngnn_csr_to_coo": (c_int32, [_P, _P, c_int64, c_int64, _P, _P]),
     "ngnn_gather_rows": (c_int32, [_P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P]),
     "ngnn_sage_agg_fwd": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, c_int64, _P]),
+    "ngnn_set_tuning": (c_int32, [c_int32, c_int32]),
     "ngnn_sage_agg_bwd": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64,
                                     c_float, _P, c_int64, _P]),
     "ngnn_sage_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64]),

@@ -41,7 +41,7 @@ __device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x;
 // index, the root / add / gate rows) is requested up front so the dependent chain per row is 3 memory round trips:
 // extents -> indices -> rows.
 template <int G, int VPL, int U>
-__global__ void __launch_bounds__(256) k_seg_reduce_v4(AggParams p) {
+__global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
   constexpr int GROUPS_PER_WARP = 32 / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);                 // lane within group
@@ -165,9 +165,108 @@ __global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Software-pipelined persistent forward kernel (the layer-1 hot case: short rows, F <= 256).
+// A sampled row costs three dependent memory round trips (extents -> indices -> feature rows) and only the
+// third moves real bytes, so a warp that walks one row at a time keeps HBM idle two thirds of the time (ncu:
+// 32 % DRAM, 43 % warps active, everything latency-bound).  Here every warp owns rows r, r+W, r+2W, ... and
+// runs a 3-stage pipeline in registers: while the feature rows of row i are in flight it has already issued
+// the index load of row i+1 and the extent / root-id loads of row i+2, so each iteration exposes ONE latency.
+// ---------------------------------------------------------------------------------------------------
+template <int VPL, int U, bool ROOT>
+__global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n = p.n_rows;
+  const int F4 = (int)(p.F >> 2);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t row1 = row0 + nwarps;
+  int beg0 = 0, end0 = 0, rid0 = 0, beg1 = 0, end1 = 0, rid1 = 0, my0 = 0;
+  if (row0 < n) { beg0 = __ldg(p.ptr + row0); end0 = __ldg(p.ptr + row0 + 1); if (ROOT) rid0 = __ldg(p.root_idx + row0); }
+  if (row1 < n) { beg1 = __ldg(p.ptr + row1); end1 = __ldg(p.ptr + row1 + 1); if (ROOT) rid1 = __ldg(p.root_idx + row1); }
+  if (row0 < n && lane < min(32, end0 - beg0)) my0 = __ldg(p.idx + beg0 + lane);
+
+  while (row0 < n) {
+    // stage A: extents + root id of the row after next
+    const int64_t row2 = row1 + nwarps;
+    int beg2 = 0, end2 = 0, rid2 = 0;
+    if (row2 < n) { beg2 = __ldg(p.ptr + row2); end2 = __ldg(p.ptr + row2 + 1); if (ROOT) rid2 = __ldg(p.root_idx + row2); }
+    // stage B: first index chunk of the next row
+    int my1 = 0;
+    if (row1 < n && lane < min(32, end1 - beg1)) my1 = __ldg(p.idx + beg1 + lane);
+
+    // stage C: gather the feature rows of row0
+    float4 acc[VPL], rootv[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = lane + v * 32;
+      acc[v] = zero4;
+      rootv[v] = (ROOT && c < F4) ? ldg_nc_f4(reinterpret_cast<const float4*>(p.x + (int64_t)rid0 * p.ld_x) + c) : zero4;
+    }
+    int my = my0;
+    for (int base = beg0; base < end0; base += 32) {
+      const int cnt = min(32, end0 - base);
+      if (base != beg0) my = (lane < cnt) ? __ldg(p.idx + base + lane) : 0;     // long rows only (deg > 32)
+      for (int j = 0; j < cnt; j += U) {
+        float4 v4[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int su = __shfl_sync(0xffffffffu, my, min(j + u, cnt - 1));
+          const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)su * p.ld_x);
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int c = lane + v * 32;
+            v4[u][v] = (c < F4 && j + u < cnt) ? ldg_nc_f4(src + c) : zero4;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) f4_add(acc[v], v4[u][v]);
+      }
+    }
+    const float scale = p.mean ? 1.0f / (float)max(end0 - beg0, 1) : 1.0f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = lane + v * 32;
+      if (c >= F4) continue;
+      float4 r = acc[v];
+      r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+      reinterpret_cast<float4*>(p.out + row0 * p.ld_out)[c] = r;
+      if (ROOT) reinterpret_cast<float4*>(p.root + row0 * p.ld_root)[c] = rootv[v];
+    }
+    // rotate the pipeline registers
+    row0 = row1; beg0 = beg1; end0 = end1; rid0 = rid1; my0 = my1;
+    row1 = row2; beg1 = beg2; end1 = end2; rid1 = rid2;
+  }
+}
+
+template <int VPL, int U, bool ROOT>
+static void launch_pipe(const AggParams& p, cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_agg_fwd_pipe<VPL, U, ROOT>, 256, 0) != cudaSuccess ||
+        blocks_per_sm < 1) {
+      cudaGetLastError();
+      blocks_per_sm = 2;
+    }
+  }
+  int64_t grid = (int64_t)kNumSMs * blocks_per_sm;                 // persistent: one resident wave
+  const int64_t need = ceil_div(p.n_rows, 8);                        // 8 warps per CTA
+  if (grid > need) grid = need;
+  k_agg_fwd_pipe<VPL, U, ROOT><<<(unsigned)grid, 256, 0, st>>>(p);
+}
+
+static int g_tune_unroll = 0;    // ngnn_set_tuning(0, u): 0 = default, else force U in {2,4,8} for F <= 128
+static int g_tune_threads = 256; // ngnn_set_tuning(1, t): CTA size 128 / 256 / 512
+static int g_tune_pipe = 1;      // ngnn_set_tuning(3, 0/1): software-pipelined persistent forward kernel
+static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 < F <= 128 (32 / 16 / 8)
+
 template <int G, int VPL, int U>
 static void launch_v4(const AggParams& p, cudaStream_t st) {
-  constexpr int T = 256;
+  const int T = g_tune_threads;
   const int64_t rows_per_block = (T / 32) * (32 / G);
   k_seg_reduce_v4<G, VPL, U><<<(unsigned)ceil_div(p.n_rows, rows_per_block), T, 0, st>>>(p);
 }
@@ -180,9 +279,33 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
   if (p.root_idx) vec = vec && (p.ld_root % 4 == 0) && is_aligned(p.root, 16);
   if (vec) {
     const int64_t F4 = p.F / 4;
+    const bool fwd_plain = p.add == nullptr && p.act_ref == nullptr;      // forward aggregation (mean [+ root gather])
+    if (fwd_plain && g_tune_pipe && F4 > 16 && F4 <= 64) {
+      if (F4 <= 32) {
+        const int u = g_tune_unroll;
+        if (p.root_idx) {
+          // measured on B200, products layer 1 (profiles/r01_agg_sweep.txt): U=6 is the sweet spot (61 % of HBM peak)
+          if (u == 8) launch_pipe<1, 8, true>(p, st); else if (u == 5) launch_pipe<1, 5, true>(p, st);
+          else if (u == 4) launch_pipe<1, 4, true>(p, st); else if (u == 3) launch_pipe<1, 3, true>(p, st);
+          else launch_pipe<1, 6, true>(p, st);
+        } else {
+          if (u == 8) launch_pipe<1, 8, false>(p, st); else if (u == 4) launch_pipe<1, 4, false>(p, st);
+          else launch_pipe<1, 6, false>(p, st);
+        }
+      } else {
+        if (p.root_idx) launch_pipe<2, 4, true>(p, st); else launch_pipe<2, 4, false>(p, st);
+      }
+      NGNN_LAUNCH_CHECK();
+      return NGNN_OK;
+    }
     if (F4 <= 8) launch_v4<8, 1, 8>(p, st);
     else if (F4 <= 16) launch_v4<16, 1, 8>(p, st);
-    else if (F4 <= 32) launch_v4<32, 1, 8>(p, st);
+    else if (F4 <= 32) {
+      const int u = g_tune_unroll;
+      if (g_tune_group == 16) { if (u == 2) launch_v4<16, 2, 2>(p, st); else if (u == 8) launch_v4<16, 2, 8>(p, st); else launch_v4<16, 2, 4>(p, st); }
+      else if (g_tune_group == 8) { if (u == 2) launch_v4<8, 4, 2>(p, st); else if (u == 8) launch_v4<8, 4, 8>(p, st); else launch_v4<8, 4, 4>(p, st); }
+      else { if (u == 2) launch_v4<32, 1, 2>(p, st); else if (u == 8) launch_v4<32, 1, 8>(p, st); else launch_v4<32, 1, 4>(p, st); }
+    }
     else if (F4 <= 64) launch_v4<32, 2, 4>(p, st);
     else if (F4 <= 128) launch_v4<32, 4, 2>(p, st);
     else launch_v4<32, 8, 1>(p, st);
@@ -200,6 +323,14 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
 using namespace ngnn;
 
 extern "C" {
+
+int32_t ngnn_set_tuning(int32_t key, int32_t value) {
+  if (key == 0) { g_tune_unroll = value; return NGNN_OK; }
+  if (key == 1 && (value == 128 || value == 256 || value == 512)) { g_tune_threads = value; return NGNN_OK; }
+  if (key == 2 && (value == 32 || value == 16 || value == 8)) { g_tune_group = value; return NGNN_OK; }
+  if (key == 3 && (value == 0 || value == 1)) { g_tune_pipe = value; return NGNN_OK; }
+  return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);
+}
 
 int32_t ngnn_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const float* x, int64_t ld_x, int64_t n_dst,
                           int64_t F, float* mean, int64_t ld_mean, const int32_t* root_idx, float* root,
