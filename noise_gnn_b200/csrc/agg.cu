@@ -37,9 +37,7 @@ struct AggParams {
 
 __device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
-// U = neighbour rows in flight per lane.  Everything that does not depend on the gathered rows (row extents, root
-// index, the root / add / gate rows) is requested up front so the dependent chain per row is 3 memory round trips:
-// extents -> indices -> rows.
+// Generic one-row-per-group kernel (all widths, optional add / gate / root gather).  U = neighbour rows in flight.
 template <int G, int VPL, int U>
 __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
   constexpr int GROUPS_PER_WARP = 32 / G;
@@ -53,28 +51,18 @@ __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
 
   const int F4 = (int)(p.F >> 2);
   const int beg = __ldg(p.ptr + row), end = __ldg(p.ptr + row + 1);
-  const int root_id = p.root_idx != nullptr ? __ldg(p.root_idx + row) : 0;
   const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
   const bool has_add = p.add != nullptr && row < p.n_add;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int c0 = 0; c0 < F4; c0 += G * VPL) {
-    float4 acc[VPL], addv[VPL], actv[VPL], rootv[VPL];
-    // first index chunk and the row-independent operands: all issued before anything is consumed
-    const int cnt0 = min(G, end - beg);
-    int my = (gl < cnt0) ? __ldg(p.idx + beg + gl) : 0;
+    float4 acc[VPL];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int c = c0 + gl + v * G;
-      acc[v] = zero4;
-      addv[v] = (has_add && c < F4) ? __ldg(reinterpret_cast<const float4*>(p.add + row * p.ld_add) + c) : zero4;
-      actv[v] = (p.act_ref != nullptr && c < F4) ? __ldg(reinterpret_cast<const float4*>(p.act_ref + row * p.ld_act) + c) : zero4;
-      rootv[v] = (p.root_idx != nullptr && c < F4) ? ldg_nc_f4(reinterpret_cast<const float4*>(p.x + (int64_t)root_id * p.ld_x) + c) : zero4;
-    }
+    for (int v = 0; v < VPL; ++v) acc[v] = zero4;
 
     for (int base = beg; base < end; base += G) {
       const int cnt = min(G, end - base);
-      if (base != beg) my = (gl < cnt) ? __ldg(p.idx + base + gl) : 0;
+      const int my = (gl < cnt) ? __ldg(p.idx + base + gl) : 0;
       for (int j = 0; j < cnt; j += U) {
         // up to U neighbour rows in flight; out-of-range slots are masked
         float4 v4[U][VPL];
@@ -101,17 +89,21 @@ __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
       if (c >= F4) continue;
       float4 r = acc[v];
       r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
-      if (has_add) f4_add(r, addv[v]);
+      if (has_add) f4_add(r, __ldg(reinterpret_cast<const float4*>(p.add + row * p.ld_add) + c));
       if (p.act_ref != nullptr) {
-        const float4 h = actv[v];
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p.act_ref + row * p.ld_act) + c);
         r.x = h.x > 0.f ? r.x * p.act_scale : 0.f;
         r.y = h.y > 0.f ? r.y * p.act_scale : 0.f;
         r.z = h.z > 0.f ? r.z * p.act_scale : 0.f;
         r.w = h.w > 0.f ? r.w * p.act_scale : 0.f;
       }
       reinterpret_cast<float4*>(p.out + row * p.ld_out)[c] = r;
-      if (p.root_idx != nullptr) reinterpret_cast<float4*>(p.root + row * p.ld_root)[c] = rootv[v];
     }
+  }
+  if (p.root_idx != nullptr) {
+    const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)__ldg(p.root_idx + row) * p.ld_x);
+    float4* dst = reinterpret_cast<float4*>(p.root + row * p.ld_root);
+    for (int c = gl; c < F4; c += G) dst[c] = ldg_nc_f4(src + c);
   }
 }
 
@@ -306,7 +298,7 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
       else if (g_tune_group == 8) { if (u == 2) launch_v4<8, 4, 2>(p, st); else if (u == 8) launch_v4<8, 4, 8>(p, st); else launch_v4<8, 4, 4>(p, st); }
       else { if (u == 2) launch_v4<32, 1, 2>(p, st); else if (u == 8) launch_v4<32, 1, 8>(p, st); else launch_v4<32, 1, 4>(p, st); }
     }
-    else if (F4 <= 64) launch_v4<32, 2, 4>(p, st);
+    else if (F4 <= 64) launch_v4<32, 2, 2>(p, st);
     else if (F4 <= 128) launch_v4<32, 4, 2>(p, st);
     else launch_v4<32, 8, 1>(p, st);
   } else {

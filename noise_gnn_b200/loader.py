@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
+from .sharding import SeedSharder
 
 
 class Data:
@@ -182,6 +183,8 @@ class NeighborLoader:
                     nodes = nodes.nonzero().view(-1)
                 nodes = nodes.to(torch.int64).view(-1)
             self.input_nodes = nodes
+            self.sharder = SeedSharder(nodes, self.batch_size, self.shuffle, self.seed, self.rank, self.world_size,
+                                       self.drop_last)
             # --- sampler capacities and workspace ---
             L = _lib.load()
             self._fan = (ctypes.c_int32 * len(self.num_neighbors))(*self.num_neighbors)
@@ -196,23 +199,17 @@ class NeighborLoader:
     # ------------------------------------------------------------------ batching
     @property
     def num_batches_global(self) -> int:
-        n = len(self.input_nodes)
-        return n // self.batch_size if self.drop_last else math.ceil(n / self.batch_size)
+        return self.sharder.num_batches_global
 
     def __len__(self) -> int:
-        return math.ceil(self.num_batches_global / self.world_size)
+        return len(self.sharder)
 
     def epoch_permutation(self, epoch: int) -> torch.Tensor:
         """Rank-agnostic seed order for an epoch: a pure function of (seed, epoch)."""
-        if not self.shuffle:
-            return self.input_nodes
-        g = torch.Generator(device="cpu")
-        g.manual_seed((self.seed * 1000003 + epoch) & 0x7FFFFFFFFFFFFFFF)
-        return self.input_nodes[torch.randperm(len(self.input_nodes), generator=g)]
+        return self.sharder.epoch_permutation(epoch)
 
     def batch_seeds(self, order: torch.Tensor, global_batch_idx: int) -> torch.Tensor:
-        b = global_batch_idx % max(self.num_batches_global, 1)      # wrap-around pads the last DP round
-        return order[b * self.batch_size:(b + 1) * self.batch_size]
+        return self.sharder.batch_seeds(order, global_batch_idx)
 
     def label_array(self, name: str) -> torch.Tensor:
         """A node attribute as a contiguous int64 [N] device array indexed by global id (for the fused step)."""
@@ -285,9 +282,9 @@ class NeighborLoader:
             order = order.to(self.device) if self.seeds_on_device else order.pin_memory()
 
             def launch(i):
-                g = i * self.world_size + self.rank
+                g = self.sharder.global_batch_index(i)
                 with torch.cuda.stream(side):
-                    pend = self._launch_sample(self.batch_seeds(order, g), epoch, g % nb)
+                    pend = self._launch_sample(self.batch_seeds(order, g), epoch, g)
                     ev = torch.cuda.Event()
                     ev.record(side)
                 return pend, ev

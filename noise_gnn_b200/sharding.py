@@ -1,0 +1,48 @@
+"""Host-side seed sharding for data-parallel mini-batch training (pure CPU logic, no CUDA).
+
+The reference is single-process (src/main.py:76-83); its loader draws ``ceil(len(input_nodes)/batch_size)``
+shuffled batches per epoch (src/pipeline.py:75-83, 152).  For N GPUs the same global batch sequence is dealt
+round-robin: rank r of R trains on global batches r, r+R, r+2R, ...  The epoch order is a pure function of
+(seed, epoch) — identical on every rank with no communication — and the last round wraps around so every rank
+issues the same number of steps (collectives stay matched).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+class SeedSharder:
+    def __init__(self, input_nodes: torch.Tensor, batch_size: int, shuffle: bool, seed: int = 1232, rank: int = 0,
+                 world_size: int = 1, drop_last: bool = False):
+        if not (0 <= rank < world_size):
+            raise ValueError(f"rank {rank} outside world of {world_size}")
+        self.input_nodes = input_nodes.to(torch.int64).view(-1).cpu()
+        self.batch_size, self.shuffle, self.seed = int(batch_size), bool(shuffle), int(seed)
+        self.rank, self.world_size, self.drop_last = int(rank), int(world_size), bool(drop_last)
+
+    @property
+    def num_batches_global(self) -> int:
+        n = len(self.input_nodes)
+        return n // self.batch_size if self.drop_last else math.ceil(n / self.batch_size)
+
+    def __len__(self) -> int:
+        """Steps per epoch on this rank (equal on all ranks)."""
+        return math.ceil(self.num_batches_global / self.world_size)
+
+    def epoch_permutation(self, epoch: int) -> torch.Tensor:
+        """Rank-agnostic seed order for an epoch: a pure function of (seed, epoch)."""
+        if not self.shuffle:
+            return self.input_nodes
+        g = torch.Generator(device="cpu")
+        g.manual_seed((self.seed * 1000003 + epoch) & 0x7FFFFFFFFFFFFFFF)
+        return self.input_nodes[torch.randperm(len(self.input_nodes), generator=g)]
+
+    def global_batch_index(self, step: int) -> int:
+        """Global batch trained by this rank at local step `step` (wraps around in the last, padded round)."""
+        return (step * self.world_size + self.rank) % max(self.num_batches_global, 1)
+
+    def batch_seeds(self, order: torch.Tensor, global_batch_idx: int) -> torch.Tensor:
+        b = global_batch_idx % max(self.num_batches_global, 1)
+        return order[b * self.batch_size:(b + 1) * self.batch_size]

@@ -17,7 +17,7 @@ from typing import Optional
 
 import torch
 
-from . import _lib, ops
+from . import _lib, dp, ops
 
 
 class FlatBuckets:
@@ -147,10 +147,8 @@ class Trainer:
 
     def optimizer_step(self):
         bk = self.buckets
-        scale = 1.0
-        if self.world_size > 1:               # DP: one all-reduce of the flat bucket, then average
-            torch.distributed.all_reduce(bk.grad, group=self.process_group)
-            scale = 1.0 / self.world_size
+        # DP: one all-reduce of the flat bucket; the 1/world averaging is folded into the Adam kernel
+        scale = dp.allreduce_mean_(bk.grad, self.process_group, self.world_size)
         ops.adam_step(bk.param, bk.grad, self.exp_avg, self.exp_avg_sq, self.step_dev, lr=self.lr, betas=self.betas,
                       eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
 

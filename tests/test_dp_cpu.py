@@ -1,0 +1,91 @@
+"""CPU tests of the multi-GPU path's host logic (world_size 2, gloo): seed sharding and the gradient all-reduce.
+
+The CUDA kernels cannot run here, so each rank computes its block and gradient with the CPU oracle; what is under
+test is the product's own sharding (noise_gnn_b200.sharding) and exchange (noise_gnn_b200.dp) code."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from noise_gnn_b200.sharding import SeedSharder
+
+
+def test_sharder_deals_global_batches_round_robin():
+    nodes = torch.arange(1000, 1103)          # 103 seeds, bs 10 -> 11 global batches
+    single = SeedSharder(nodes, 10, shuffle=True, seed=1232)
+    assert single.num_batches_global == 11 and len(single) == 11
+    order = single.epoch_permutation(3)
+    assert sorted(order.tolist()) == nodes.tolist()
+    assert torch.equal(order, SeedSharder(nodes, 10, True, 1232, rank=1, world_size=4).epoch_permutation(3))   # rank-agnostic
+    assert not torch.equal(order, single.epoch_permutation(4))
+    for R in (2, 3, 4, 8):
+        shards = [SeedSharder(nodes, 10, True, 1232, rank=r, world_size=R) for r in range(R)]
+        steps = len(shards[0])
+        assert all(len(s) == steps for s in shards) and steps == -(-11 // R)     # equal step counts on every rank
+        seen = [s.global_batch_index(i) for i in range(steps) for s in shards]
+        assert seen[:11] == list(range(11))                                       # r, r+R, r+2R, ... covers the epoch in order
+        assert all(g < 11 for g in seen)                                          # the padded round wraps around
+    last = single.batch_seeds(order, 10)
+    assert len(last) == 3                                                         # partial last batch, as PyG's loader
+    assert len(SeedSharder(nodes, 10, True, drop_last=True)) == 10
+    with pytest.raises(ValueError):
+        SeedSharder(nodes, 10, True, rank=2, world_size=2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from noise_gnn_b200 import dp
+    from noise_gnn_b200.synthetic import make_dataset
+    from oracle import sage_oracle, sampler, structure
+    data, sh, train_idx = make_dataset("pubmed", scale=0.05, device="cpu")
+    colptr, row, _ = structure.coo_to_csr(data.edge_index[0].numpy(), data.edge_index[1].numpy(), data.num_nodes)
+    cs = sampler.CSampler(colptr, row)
+    fan, bs = [5, 5], 8
+    seeds_all = torch.arange(64)
+    torch.manual_seed(7)
+    model = sage_oracle.SAGERef(sh.features, 16, sh.classes, 2, dropout=0.0, dtype=torch.float64)
+
+    def grad_of_batch(g, order, sharder):
+        blk = cs.sample(sharder.batch_seeds(order, g).numpy(), fan, seed=1232, epoch=0, batch_idx=g)
+        n_id = torch.from_numpy(blk.n_id.astype(np.int64))
+        ei = torch.from_numpy(structure.csr_to_coo(blk.rowptr, blk.col))
+        model.zero_grad()
+        out = model(data.x[n_id].double(), ei)[:bs]
+        torch.nn.functional.cross_entropy(out, data.y[n_id][:bs].view(-1)).backward()
+        return torch.cat([p.grad.view(-1) for p in model.parameters()]).clone()
+
+    sharder = SeedSharder(seeds_all, bs, shuffle=True, seed=1232, rank=rank, world_size=world)
+    order = sharder.epoch_permutation(0)
+    g_mine = sharder.global_batch_index(0)
+    bucket = grad_of_batch(g_mine, order, sharder)
+    scale = dp.allreduce_mean_(bucket, world_size=world)
+    reduced = bucket * scale
+    # single-process reference: the mean of the gradients of global batches 0..world-1
+    solo = SeedSharder(seeds_all, bs, shuffle=True, seed=1232)
+    want = sum(grad_of_batch(g, order, solo) for g in range(world)) / world
+    torch.save({"reduced": reduced, "want": want, "g": g_mine, "scale": scale}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_single_rank(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    assert [r["g"] for r in res] == [0, 1]
+    assert all(abs(r["scale"] - 0.5) < 1e-12 for r in res)
+    assert torch.equal(res[0]["reduced"], res[1]["reduced"])                  # every rank holds the same averaged gradient
+    assert torch.allclose(res[0]["reduced"], res[0]["want"], rtol=1e-12, atol=1e-14)
