@@ -119,6 +119,7 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
     assert lib.ngnn_device_supported() == 1, "libngnn_b200.so is sm_100a only"
@@ -218,7 +219,7 @@ def run_ours(args):
         _lib.call("ngnn_probe_enable", 0)
     agg_bytes = [agg_l1_bytes(t, n_dst, e1, sh.features) for t, (n_dst, e1) in zip(touched, ext)]
     achieved = (sum(agg_bytes) / len(agg_bytes)) / (sum(agg_ms) / len(agg_ms) * 1e-3) / 1e9 if agg_ms else None
-    roofline = {"kernel": "k_seg_reduce_v4 (K-AGG layer 1: mean of sampled in-neighbours + root gather from the resident table)",
+    roofline = {"kernel": "k_agg_fwd_pipe<1,6,true> (K-AGG layer 1: mean of sampled in-neighbours + root gather from the resident table)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs if achieved else None, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
