@@ -118,6 +118,9 @@ int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, in
                            float drop_p, uint64_t seed, uint64_t offset,
                            float* out, int64_t ld_out, int32_t* path,
                            void* ws, size_t ws_bytes, ngnn_stream_t stream);
+/* Development aid: when set to a device buffer of >= 8 + 8*K-blocks int64, CTA (0,0) of the tcgen05 GEMM records
+ * clock64() per pipeline event (profiles/trace_gemm.py).  NULL disables.                                      */
+int32_t ngnn_debug_set_trace(void* device_buffer);
 /* 0 = automatic dispatch (default), 1 = force the SIMT fp32 kernels (tests / A-B timing). */
 int32_t ngnn_set_gemm_path(int32_t mode);
 

@@ -32,6 +32,7 @@ SIGNATURES = {
     "ngnn_sage_gemm_fwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, c_int32,
                                      c_float, c_uint64, c_uint64, _P, c_int64, _P, _P, c_size_t, _P]),
     "ngnn_set_gemm_path": (c_int32, [c_int32]),
+    "ngnn_debug_set_trace": (c_int32, [_P]),
     "ngnn_sage_dgrad_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ngnn_sage_dgrad": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P,
                                   c_size_t, _P]),

@@ -314,6 +314,8 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
 
 using namespace ngnn;
 
+extern "C" int32_t ngnn_set_gemm_tile(int32_t bn_max);   // gemm.cu
+
 extern "C" {
 
 int32_t ngnn_set_tuning(int32_t key, int32_t value) {
@@ -321,6 +323,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 1 && (value == 128 || value == 256 || value == 512)) { g_tune_threads = value; return NGNN_OK; }
   if (key == 2 && (value == 32 || value == 16 || value == 8)) { g_tune_group = value; return NGNN_OK; }
   if (key == 3 && (value == 0 || value == 1)) { g_tune_pipe = value; return NGNN_OK; }
+  if (key == 4 && (value == 128 || value == 256)) return ngnn_set_gemm_tile(value);
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);
 }
 

@@ -100,6 +100,13 @@ int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const 
   return NGNN_OK;
 }
 
+int32_t ngnn_set_gemm_tile(int32_t bn_max) { g_tc_bn_max = bn_max; return NGNN_OK; }   // reached through ngnn_set_tuning(4, .)
+
+int32_t ngnn_debug_set_trace(void* device_buffer) {
+  g_tc_trace = reinterpret_cast<long long*>(device_buffer);
+  return NGNN_OK;
+}
+
 int32_t ngnn_set_gemm_path(int32_t mode) {
   NGNN_REQUIRE(mode == 0 || mode == 1, NGNN_E_INVALID, "set_gemm_path: mode must be 0 (auto) or 1 (force SIMT)");
   g_force_simt = mode;

@@ -126,6 +126,41 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// Coalesced tile store for the epilogue warps.  After tcgen05.ld each lane holds consecutive columns of ITS row, so
+// a direct store makes every warp-level instruction touch 32 different lines with 16 bytes each.  Instead the warp
+// transposes through a private 32 x 32 staging patch in shared memory (row stride 36 floats: conflict-free for
+// 128-bit accesses) and writes 4 rows x 128 contiguous bytes (full lines) per instruction.
+// `r` = this lane's finished values for columns [nb, nb+32) of row (row0 + lane); columns >= n_cols are dropped.
+constexpr int EPI_STRIDE = 36;
+constexpr int EPI_PATCH = 32 * EPI_STRIDE;      // floats per warp
+__device__ __forceinline__ void epilogue_store32(float* stage /*warp-private [32][36]*/, const float (&r)[32], float* out,
+                                                 int64_t ld_out, int64_t row0, int64_t n_rows, int32_t nb, int32_t n_cols,
+                                                 bool vec_ok, int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(stage + lane * EPI_STRIDE + 4 * g) = make_float4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+  __syncwarp();
+  const int sub = lane >> 3, part = lane & 7;          // 4 rows per instruction, 8 lanes (128 B) per row
+#pragma unroll
+  for (int rr = 0; rr < 32; rr += 4) {
+    const int lr = rr + sub;
+    const float4 v = *reinterpret_cast<const float4*>(stage + lr * EPI_STRIDE + 4 * part);
+    const int64_t m = row0 + lr;
+    const int32_t n4 = nb + 4 * part;
+    if (m < n_rows && n4 < n_cols) {
+      float* dst = out + m * ld_out + n4;
+      if (vec_ok && n4 + 3 < n_cols) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) if (n4 + jj < n_cols) dst[jj] = e[jj];
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ----------------------------------------------------------------------------- weight prep
 // Packs up to two [R, C] fp32 weight matrices side by side along K into hi / lo planes [R_out, Kpack]:
 //   transpose == 0: out[r, seg*Cpad + c] = W_seg[r, c]           (forward:  B = [W_l | W_r], rows = O, K = F)
@@ -173,16 +208,28 @@ struct TcGemmParams {
   int32_t kblocks1, kblocks2; // K-blocks of operand pair 1 / 2
   int32_t b_koff2;            // k offset (floats) of pair 2 in the packed B planes
   int32_t stages;
-  int32_t tiles_per_seg;      // N tiles per segment (grid.y = tiles_per_seg * num_segs)
+  int32_t tiles_per_seg;      // N tiles per segment
+  int32_t num_segs;
   TcSegment seg[2];
   const float* bias;
   const int32_t* rowptr;
   int32_t act;
   float drop_p;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  long long* trace;           // debug: CTA (0,0) records clock64 per K-block: [kb][0..5] (see profiles/trace_gemm.py)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+static long long* g_tc_trace = nullptr;   // ngnn_debug_set_trace
+
+// Persistent, warp-specialised:  warp 0 = TMA producer, warp 1 = MMA issuer (owns TMEM), warps 2-5 = converters
+// (hi/lo split of the A tile in shared memory), warps 6-9 = epilogue.  Two TMEM accumulator buffers let the epilogue
+// of tile j (TMEM -> registers -> smem transpose -> full-line global stores) overlap the main loop of tile j+1; the
+// smem ring runs continuously across tile boundaries.
+constexpr int TG_THREADS = 320;
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
           const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -191,27 +238,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
   const uint32_t a_bytes = TC_BM * TC_BK * 4;                 // 16 KB
   const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 4;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
-  uint64_t* full_raw = reinterpret_cast<uint64_t*>(bar_base);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);     // 4 warps x [32][36] floats
+  float* bias_s = epi_stage + 4 * EPI_PATCH;                                               // [288]
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(bias_s + 288);
   uint64_t* full_conv = full_raw + TC_MAX_STAGES;
   uint64_t* empty = full_conv + TC_MAX_STAGES;
-  uint64_t* tmem_full = empty + TC_MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + TC_MAX_STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int32_t m0 = blockIdx.x * TC_BM;
-  const int32_t seg_id = blockIdx.y / p.tiles_per_seg;
-  const int32_t n_tile = blockIdx.y - seg_id * p.tiles_per_seg;
-  const TcSegment sg = p.seg[seg_id];
-  const int32_t n0 = n_tile * p.BN;                            // first output column of this tile within the segment
   const int32_t KB = p.kblocks1 + p.kblocks2;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+  const int32_t m_tiles = (p.M + TC_BM - 1) / TC_BM;
+  const int32_t total_tiles = m_tiles * p.tiles_per_seg * p.num_segs;
+  uint32_t buf_cols = 32;
+  while (buf_cols < (uint32_t)p.BN) buf_cols <<= 1;
+  const uint32_t tmem_cols = 2 * buf_cols;
+  long long* tr = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 128); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -220,114 +269,170 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> (m tile, segment, n tile): consecutive tiles walk M so that co-running CTAs share the same B tile in L2
+  auto decode = [&](int32_t tile, int32_t& m0, int32_t& seg_id, int32_t& n0) {
+    const int32_t n_idx = tile / m_tiles;
+    m0 = (tile - n_idx * m_tiles) * TC_BM;
+    seg_id = n_idx / p.tiles_per_seg;
+    n0 = (n_idx - seg_id * p.tiles_per_seg) * p.BN;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int32_t kb = 0; kb < KB; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        mbar_arrive_expect_tx(&full_raw[s], a_bytes + 2 * b_bytes);
-        const bool first = kb < p.kblocks1;
-        const int32_t ka = (first ? kb : kb - p.kblocks1) * TC_BK;
-        const int32_t kbk = first ? ka : p.b_koff2 + ka;
-        tma_load_2d(st, first ? &tmA1 : &tmA2, &full_raw[s], ka, m0);
-        tma_load_2d(st + 2 * a_bytes, &tmBhi, &full_raw[s], kbk, sg.b_row0 + n0);
-        tma_load_2d(st + 2 * a_bytes + b_bytes, &tmBlo, &full_raw[s], kbk, sg.b_row0 + n0);
+      uint32_t it = 0;
+      for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int32_t m0, seg_id, n0;
+        decode(tile, m0, seg_id, n0);
+        const int32_t b_row = p.seg[seg_id].b_row0 + n0;
+        for (int32_t kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          if (tr && it < 32) tr[8 + it * 8 + 0] = clock64();
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&full_raw[s], a_bytes + 2 * b_bytes);
+          const bool first = kb < p.kblocks1;
+          const int32_t ka = (first ? kb : kb - p.kblocks1) * TC_BK;
+          const int32_t kbk = first ? ka : p.b_koff2 + ka;
+          tma_load_2d(st, first ? &tmA1 : &tmA2, &full_raw[s], ka, m0);
+          tma_load_2d(st + 2 * a_bytes, &tmBhi, &full_raw[s], kbk, b_row);
+          tma_load_2d(st + 2 * a_bytes + b_bytes, &tmBlo, &full_raw[s], kbk, b_row);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = umma_idesc_tf32(TC_BM, (uint32_t)p.BN);
-    for (int32_t kb = 0; kb < KB; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-      mbar_wait(&full_conv[s], ph);
+    uint32_t it = 0, j = 0;
+    for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const uint32_t ab = j & 1u;
+      mbar_wait(&tmem_empty[ab], ((j >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator buffer
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + 2 * a_bytes, b_lo = b_hi + b_bytes;
+      const uint32_t tmem_d = tmem_base + ab * buf_cols;
+      for (int32_t kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        mbar_wait(&full_conv[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          if (tr && it < 32) tr[8 + it * 8 + 3] = clock64();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + 2 * a_bytes, b_lo = b_hi + b_bytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint32_t koff = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle atom
-          const uint64_t dah = umma_desc_k_sw128(a_hi + koff), dal = umma_desc_k_sw128(a_lo + koff);
-          const uint64_t dbh = umma_desc_k_sw128(b_hi + koff), dbl = umma_desc_k_sw128(b_lo + koff);
-          umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint32_t koff = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle atom
+            const uint64_t dah = umma_desc_k_sw128(a_hi + koff), dal = umma_desc_k_sw128(a_lo + koff);
+            const uint64_t dbh = umma_desc_k_sw128(b_hi + koff), dbl = umma_desc_k_sw128(b_lo + koff);
+            umma_tf32(tmem_d, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+          }
+          umma_commit(&empty[s]);                          // stage reusable once these MMAs have read it
+          if (kb == KB - 1) umma_commit(&tmem_full[ab]);   // accumulator complete
+          if (tr && it < 32) tr[8 + it * 8 + 4] = clock64();
         }
-        umma_commit(&empty[s]);                      // stage reusable once these MMAs have read it
-        if (kb == KB - 1) umma_commit(tmem_full);    // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== converter warps (2..5) =====================
     const int t = threadIdx.x - 64;                  // 0..127
-    for (int32_t kb = 0; kb < KB; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-      mbar_wait(&full_raw[s], ph);
-      float4* hi4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-      float4* lo4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
+    uint32_t it = 0;
+    for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int32_t kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        mbar_wait(&full_raw[s], ph);
+        if (tr && t == 0 && it < 32) tr[8 + it * 8 + 1] = clock64();
+        float4* hi4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+        float4* lo4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
 #pragma unroll
-      for (int j = 0; j < (TC_BM * TC_BK / 4) / 128; ++j) {
-        const int i = t + 128 * j;
-        const float4 x = hi4[i];
-        float4 h, l;
-        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-        hi4[i] = h;
-        lo4[i] = l;
+        for (int q4 = 0; q4 < (TC_BM * TC_BK / 4) / 128; ++q4) {
+          const int i = t + 128 * q4;
+          const float4 x = hi4[i];
+          float4 h, l;
+          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+          hi4[i] = h;
+          lo4[i] = l;
+        }
+        fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&full_conv[s]);
+        if (tr && t == 0 && it < 32) tr[8 + it * 8 + 2] = clock64();
       }
-      fence_proxy_async_smem();                      // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_conv[s]);
     }
-    // ===================== epilogue =====================
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+  } else {
+    // ===================== epilogue warps (6..9) =====================
+    const int et = threadIdx.x - 192;                // 0..127
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int64_t m = (int64_t)m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
-    float rs = 1.0f;
-    if (sg.scale_rows && p.rowptr != nullptr && row_ok)
-      rs = 1.0f / (float)max(__ldg(p.rowptr + m + 1) - __ldg(p.rowptr + m), 1);
+    float* stage = epi_stage + (warp - 6) * EPI_PATCH;
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-    float* orow = sg.out + m * sg.ld_out;
-    const bool vec_ok = ((sg.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
-    for (int32_t c = 0; c < p.BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      const int32_t nb = n0 + c;
-      if (!row_ok || nb >= sg.n_cols) continue;
+    uint32_t j = 0;
+    for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      int32_t m0, seg_id, n0;
+      decode(tile, m0, seg_id, n0);
+      const TcSegment sg = p.seg[seg_id];
+      const uint32_t ab = j & 1u;
+      // bias of this tile's columns -> smem (the previous tile's readers are past their last use: barrier first)
+      epi_bar_sync();
+      for (int i = et; i < 288; i += 128) bias_s[i] = (p.bias != nullptr && n0 + i < sg.n_cols) ? __ldg(p.bias + n0 + i) : 0.f;
+      epi_bar_sync();
+      const int64_t row0 = (int64_t)m0 + q * 32;
+      const int64_t m = row0 + lane;
+      const bool row_ok = m < p.M;
+      float rs = 1.0f;
+      if (sg.scale_rows && p.rowptr != nullptr && row_ok)
+        rs = 1.0f / (float)max(__ldg(p.rowptr + m + 1) - __ldg(p.rowptr + m), 1);
+      const bool vec_ok = ((sg.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
+      mbar_wait(&tmem_full[ab], (j >> 1) & 1u);
+      tc_fence_after();
+      if (tr && et == 0 && j == 0) tr[1] = clock64();
+      const uint32_t tmem_d = tmem_base + ab * buf_cols + ((uint32_t)(q * 32) << 16);
+      for (int32_t c = 0; c < p.BN; c += 32) {
+        const int32_t nb = n0 + c;
+        const bool live = nb < sg.n_cols;            // warp-uniform
+        uint32_t v[32];
+        if (live) {
+          uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
+          uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
+          tmem_ld16(tmem_d + (uint32_t)c, v0);
+          if (c + 16 < p.BN) tmem_ld16(tmem_d + (uint32_t)(c + 16), v1);
+          else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int32_t n4 = nb + 4 * g;
-        if (n4 >= sg.n_cols) break;
-        float r[4];
-        uint32_t keep = 0xFu;
-        if (p.drop_p > 0.f) keep = dropout_keep4((uint32_t)m, (uint32_t)(n4 >> 2), p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float x = __uint_as_float(v[4 * g + j]);
-          if (p.bias != nullptr && n4 + j < sg.n_cols) x += __ldg(p.bias + n4 + j);
-          x *= rs;
-          if (p.act == NGNN_ACT_RELU) x = fmaxf(x, 0.f);
-          if (p.drop_p > 0.f) x = ((keep >> j) & 1u) ? x * keep_scale : 0.f;
-          r[j] = x;
+            for (int jj = 0; jj < 16; ++jj) v1[jj] = 0u;
+          }
         }
-        if (vec_ok && n4 + 3 < sg.n_cols) {
-          *reinterpret_cast<float4*>(orow + n4) = make_float4(r[0], r[1], r[2], r[3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (n4 + j < sg.n_cols) orow[n4 + j] = r[j];
+        if (c + 32 >= p.BN) {                          // last TMEM read of this tile done: hand the buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[ab]);
         }
+        if (!live) continue;
+        float r[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int32_t n4 = nb + 4 * g;
+          uint32_t keep = 0xFu;
+          if (p.drop_p > 0.f && row_ok && n4 < sg.n_cols)
+            keep = dropout_keep4((uint32_t)m, (uint32_t)(n4 >> 2), p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr);
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * g);     // smem broadcast
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float x = (__uint_as_float(v[4 * g + jj]) + bb[jj]) * rs;
+            if (p.act == NGNN_ACT_RELU) x = fmaxf(x, 0.f);
+            if (p.drop_p > 0.f) x = ((keep >> jj) & 1u) ? x * keep_scale : 0.f;
+            r[4 * g + jj] = x;
+          }
+        }
+        epilogue_store32(stage, r, sg.out, sg.ld_out, row0, p.M, nb, sg.n_cols, vec_ok, lane);
       }
+      if (tr && et == 0 && j == 0) tr[3] = clock64();
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
@@ -371,18 +476,21 @@ static inline bool tma_addressable(const float* p, int64_t ld) { return p != nul
 
 static inline int32_t round_up_i(int64_t x, int64_t a) { return (int32_t)((x + a - 1) / a * a); }
 
+static int g_tc_bn_max = 256;   // ngnn_set_tuning(4, 128|256): widest N tile (256 -> 2 smem stages, 128 -> 3)
+
 struct TcPlan {
   int32_t BN, tiles_per_seg, stages;
   uint32_t smem_bytes;
 };
 static inline TcPlan tc_plan(int64_t n_cols) {
   TcPlan pl;
-  pl.BN = n_cols >= 256 ? 256 : round_up_i(n_cols, 16);
+  pl.BN = n_cols >= g_tc_bn_max ? g_tc_bn_max : round_up_i(n_cols, 16);
   pl.tiles_per_seg = (int32_t)ceil_div(n_cols, pl.BN);
   const uint32_t stage = 2u * TC_BM * TC_BK * 4u + 2u * (uint32_t)pl.BN * TC_BK * 4u;
-  int st = (int)((TC_SMEM_LIMIT - 2048u) / stage);
+  const uint32_t fixed = 1024u /*align*/ + 4u * EPI_PATCH * 4u /*epilogue staging*/ + 288u * 4u /*bias*/ + 256u /*barriers*/;
+  int st = (int)((TC_SMEM_LIMIT - fixed) / stage);
   pl.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
-  pl.smem_bytes = (uint32_t)pl.stages * stage + 1024u /*align*/ + 256u /*barriers*/;
+  pl.smem_bytes = (uint32_t)pl.stages * stage + fixed;
   return pl;
 }
 
@@ -404,8 +512,12 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
     NGNN_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(p.M, TC_BM), (unsigned)(pl.tiles_per_seg * num_segs));
-  k_tc_gemm<<<grid, TC_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, p);
+  TcGemmParams pp = p;
+  pp.trace = g_tc_trace;
+  pp.num_segs = num_segs;
+  const int64_t tiles = ceil_div(p.M, TC_BM) * pl.tiles_per_seg * num_segs;
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);      // persistent: one CTA per SM
+  k_tc_gemm<<<grid, TG_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, pp);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;
 }
@@ -639,27 +751,31 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
       fence_proxy_async_smem();
       mbar_arrive(&full_conv[s]);
     }
-    // epilogue: partial tile -> global
+    // epilogue: partial tile -> global (coalesced through a shared-memory staging patch)
     const int q = warp & 3;
-    const int64_t o = (int64_t)o0 + q * 32 + lane;
-    float* orow = sg.out + (int64_t)blockIdx.z * sg.split_stride + o * sg.n_cols;
+    const int64_t row0 = (int64_t)o0 + q * 32;
+    float* obase = sg.out + (int64_t)blockIdx.z * sg.split_stride;
+    const bool vec_ok = ((sg.n_cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * EPI_PATCH;
     if (KB > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
-    for (int32_t c = 0; c < p.BN; c += 16) {
-      uint32_t v[16];
-      if (KB > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      else {
+    for (int32_t c = 0; c < p.BN; c += 32) {
+      if (f0 + c >= sg.n_cols) break;
+      uint32_t v[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
+      if (KB > 0) {
+        uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
+        uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v0);
+        if (c + 16 < p.BN) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c + 16), v1);
       }
-      if (o >= p.O) continue;
+      float r[32];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int32_t f = f0 + c + j;
-        if (f < sg.n_cols) orow[f] = __uint_as_float(v[j]);
-      }
+      for (int jj = 0; jj < 32; ++jj) r[jj] = __uint_as_float(v[jj]);
+      epilogue_store32(stage, r, obase, sg.n_cols, row0, p.O, f0 + c, sg.n_cols, vec_ok, lane);
     }
   }
   tc_fence_before();

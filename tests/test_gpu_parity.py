@@ -95,13 +95,17 @@ def test_agg_fwd_matches_oracle(dev, F):
 def test_agg_fwd_long_rows_and_determinism(dev):
     from noise_gnn_b200 import ops
     n, F = 64, 100
-    ei = torch.stack([torch.randint(0, n, (5000,)), torch.zeros(5000, dtype=torch.long)])   # one row of degree 5000
-    x = torch.randn(n, F)
+    g = torch.Generator().manual_seed(77)
+    ei = torch.stack([torch.randint(0, n, (5000,), generator=g), torch.zeros(5000, dtype=torch.long)])   # one row of degree 5000
+    x = torch.randn(n, F, generator=g)
     blk = ops.coo_to_csr(ei.to(dev), n)
     a = ops.agg_fwd(blk.rowptr, blk.col, x.to(dev), n)
     b = ops.agg_fwd(blk.rowptr, blk.col, x.to(dev), n)
-    assert torch.equal(a, b)                   # atomic-free => bitwise reproducible
-    assert rel_err(a, sage_oracle.mean_aggregate(x.double(), ei)) < RTOL
+    assert torch.equal(a, b), "aggregation is not bitwise reproducible"       # atomic-free, fixed summation order
+    # a 5000-term fp32 sum: compare with the error the fp32 CPU oracle itself makes against fp64
+    want = sage_oracle.mean_aggregate(x.double(), ei)
+    err_ref = rel_err(sage_oracle.mean_aggregate(x, ei), want)
+    assert rel_err(a, want) < max(RTOL, 4 * err_ref), (rel_err(a, want), err_ref)
 
 
 @pytest.mark.parametrize("F", [64, 100, 256, 47])
