@@ -221,6 +221,11 @@ typedef struct {
   int32_t        num_hops;    /* H */
   const int32_t* hop_nodes;   /* (host) [H+1] cumulative nodes, hop_nodes[0] = batch size */
   const int32_t* hop_edges;   /* (host) [H+1] cumulative edges, hop_edges[0] = 0 */
+  /* Optional precomputed transposes of hop prefixes (ngnn_csr_transpose of the first hop_edges[b] edges over
+   * hop_nodes[b] columns), indexed by b = 1..H; NULL entries are computed inside ngnn_sage_step.  The loader
+   * builds them on its side stream so the sort is off the step's critical path.                           */
+  const int32_t* colptr_t[8];
+  const int32_t* row_t[8];
 } ngnn_block_t;
 
 int64_t ngnn_sage_num_params(const ngnn_sage_model_t* model);

@@ -66,7 +66,8 @@ class SageModel(ctypes.Structure):      # ngnn_sage_model_t
 
 class BlockDesc(ctypes.Structure):      # ngnn_block_t
     _fields_ = [("rowptr", c_void_p), ("col", c_void_p), ("col_global", c_void_p), ("n_id", c_void_p),
-                ("num_hops", c_int32), ("hop_nodes", ctypes.POINTER(c_int32)), ("hop_edges", ctypes.POINTER(c_int32))]
+                ("num_hops", c_int32), ("hop_nodes", ctypes.POINTER(c_int32)), ("hop_edges", ctypes.POINTER(c_int32)),
+                ("colptr_t", c_void_p * 8), ("row_t", c_void_p * 8)]
 
 
 _lib = None

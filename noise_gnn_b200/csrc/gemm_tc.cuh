@@ -476,7 +476,8 @@ static inline bool tma_addressable(const float* p, int64_t ld) { return p != nul
 
 static inline int32_t round_up_i(int64_t x, int64_t a) { return (int32_t)((x + a - 1) / a * a); }
 
-static int g_tc_bn_max = 256;   // ngnn_set_tuning(4, 128|256): widest N tile (256 -> 2 smem stages, 128 -> 3)
+static int g_tc_bn_max = 128;   // ngnn_set_tuning(4, 128|256): widest N tile.  128 -> 3 smem stages (measured 2x faster
+                                // than 256 -> 2 stages on the products layer-1 shape: TMA latency is the limiter)
 
 struct TcPlan {
   int32_t BN, tiles_per_seg, stages;

@@ -213,11 +213,19 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
     rc = ngnn_sage_dgrad(F32(lp.dy), lp.ldo, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows, lp.F, lp.O,
                          F32(pl.dmean), lp.F, F32(pl.droot), lp.F, base + pl.dgrad_ws, pl.dgrad_ws_bytes, stream);
     if (rc != NGNN_OK) return rc;
-    rc = ngnn_csr_transpose(block->rowptr, block->col, n_rows, e_lim, lp.n_src, I32(lp.colptr_t), I32(lp.row_t), I32(lp.perm_t),
-                            base + pl.sort_ws, pl.sort_ws_bytes, stream);
-    if (rc != NGNN_OK) return rc;
+    const int32_t* colptr_t = I32(lp.colptr_t);
+    const int32_t* row_t = I32(lp.row_t);
+    const int hop_b = (L - 1 - i) + 1 < block->num_hops ? (L - 1 - i) + 1 : block->num_hops;   // hop prefix this layer's edges span
+    if (hop_b < 8 && block->colptr_t[hop_b] != nullptr && block->row_t[hop_b] != nullptr) {
+      colptr_t = block->colptr_t[hop_b];           // built by the loader on its side stream
+      row_t = block->row_t[hop_b];
+    } else {
+      rc = ngnn_csr_transpose(block->rowptr, block->col, n_rows, e_lim, lp.n_src, I32(lp.colptr_t), I32(lp.row_t), I32(lp.perm_t),
+                              base + pl.sort_ws, pl.sort_ws_bytes, stream);
+      if (rc != NGNN_OK) return rc;
+    }
     // dY of the previous layer = gate(prev output) * (transpose-sum of dmean + droot on the root rows)
-    rc = ngnn_sage_agg_bwd(I32(lp.colptr_t), I32(lp.row_t), F32(pl.dmean), lp.F, lp.n_src, lp.F, F32(pl.droot), lp.F, n_rows,
+    rc = ngnn_sage_agg_bwd(colptr_t, row_t, F32(pl.dmean), lp.F, lp.n_src, lp.F, F32(pl.droot), lp.F, n_rows,
                            F32(prev.out), prev.ldo, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.ldo, stream);
     if (rc != NGNN_OK) return rc;
   }

@@ -151,6 +151,7 @@ class NeighborLoader:
         self.seed, self.rank, self.world_size = int(seed), int(rank), int(world_size)
         self.return_e_id = return_e_id
         self.seeds_on_device = bool(seeds_on_device)   # keep each epoch's seed order in HBM (no per-step H2D at all)
+        self.transpose_hops = 0     # hop prefixes 1..k whose CSC transpose the iterator builds on its side stream (Trainer sets it)
         self.epoch = 0
         self.data = data
         N = data.num_nodes
@@ -293,10 +294,21 @@ class NeighborLoader:
             for i in range(steps):
                 pend, ev = pending
                 ev.synchronize()                                   # host needs the block extents of batch i
-                pending = launch(i + 1) if i + 1 < steps else None
+                batch = self._finish_sample(pend)
                 main = torch.cuda.current_stream()
+                if self.transpose_hops > 0:
+                    # the backward's CSC transposes only depend on the block: build them here, off the step's critical
+                    # path (they overlap the previous step still executing on the main stream)
+                    blk = batch.block
+                    with torch.cuda.stream(side):
+                        for b in range(1, min(self.transpose_hops, len(blk.hop_nodes) - 1) + 1):
+                            for t in blk.transpose(blk.hop_edges[b], blk.hop_nodes[b]):
+                                t.record_stream(main)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                pending = launch(i + 1) if i + 1 < steps else None
                 main.wait_event(ev)
                 for k in ("seeds", "n_id", "rowptr", "col", "colg", "epos", "counts"):
                     if pend[k] is not None:
                         pend[k].record_stream(main)                # allocated on the side stream, consumed on main
-                yield self._finish_sample(pend)
+                yield batch

@@ -131,6 +131,13 @@ class Trainer:
         hop_e = (ctypes.c_int32 * (H + 1))(*blk.hop_edges)
         bd = _lib.BlockDesc(blk.rowptr.data_ptr(), blk.col.data_ptr(), blk.col_global.data_ptr(), blk.n_id.data_ptr(), H,
                             hop_n, hop_e)
+        if train:
+            need = min(self._cfg["num_layers"] - 1, H)
+            loader.transpose_hops = max(loader.transpose_hops, need)      # later batches arrive with them prebuilt
+            for b in range(1, min(need, 7) + 1):
+                pre = blk._t.get((blk.hop_edges[b], blk.hop_nodes[b]))
+                if pre is not None:
+                    bd.colptr_t[b], bd.row_t[b] = pre[0].data_ptr(), pre[1].data_ptr()
         tgt = loader.label_array(target_attr) if target_attr else None
         lab = loader.label_array(label_attr) if label_attr else None
         logits = None

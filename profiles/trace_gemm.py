@@ -9,7 +9,10 @@ import torch  # noqa: E402
 from noise_gnn_b200 import _lib, ops  # noqa: E402
 
 dev = torch.device("cuda", 0)
-for (n, F, O) in ((77000, 100, 256), (8200, 256, 256), (512, 256, 47)):
+import itertools
+for bn, (n, F, O) in itertools.product((256, 128), ((77000, 100, 256), (8200, 256, 256))):
+    _lib.call('ngnn_set_tuning', 4, bn)
+    print('BN_max', bn)
     a_l, a_r = torch.randn(n, F, device=dev), torch.randn(n, F, device=dev)
     w_l, w_r, b = torch.randn(O, F, device=dev), torch.randn(O, F, device=dev), torch.randn(O, device=dev)
     for _ in range(3):
@@ -27,10 +30,6 @@ for (n, F, O) in ((77000, 100, 256), (8200, 256, 256), (512, 256, 47)):
     kb = 2 * ((F + 31) // 32)
     print(f"n={n} F={F} O={O}: kernel+prep {s.elapsed_time(e) * 1e3:.1f} us; CTA0: tmem_full at {t[1] - t0} cyc, epilogue done at {t[3] - t0} cyc, {kb} K-blocks")
     print("  kb: producer_go  raw_landed  conv_done  mma_start  mma_issued   (cycles since CTA start)")
-    for k in range(kb):
+    for k in range(min(32, kb * 4)):
         r = t[8 + 8 * k: 8 + 8 * k + 5]
         print(f"  {k:2d}: " + "  ".join(f"{v - t0:9d}" for v in r))
-    print("  epilogue chunk: before_ld  after_ld  after_math  after_store (cycles since tmem_full)")
-    for c in range(min(16, (O + 15) // 16)):
-        r = t[520 + 4 * c: 520 + 4 * c + 4]
-        print(f"  {c:2d}: " + "  ".join(f"{v - t[1]:9d}" for v in r))
