@@ -221,7 +221,10 @@ def run_ours(args):
     achieved = (sum(agg_bytes) / len(agg_bytes)) / (sum(agg_ms) / len(agg_ms) * 1e-3) / 1e9 if agg_ms else None
     roofline = {"kernel": "k_agg_fwd_pipe<1,6,true> (K-AGG layer 1: mean of sampled in-neighbours + root gather from the resident table)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs if achieved else None, "traffic": None,
+                "frac": achieved / peak_gbs if achieved else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on a products layer-1 block, one
+                # ncu --set full capture (profiles/r01_ncu_agg_pipe_summary.txt): 216.9 MB + 11.4 MB
+                "traffic": 228.3e6,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "avg_launch_us": 1e3 * sum(agg_ms) / len(agg_ms) if agg_ms else None,
                 "algorithmic_bytes_per_launch": sum(agg_bytes) / len(agg_bytes) if agg_bytes else None,

@@ -24,8 +24,8 @@ static int32_t wgrad_splits(int64_t n, int64_t F, int64_t O) {
   return (int32_t)s;
 }
 static int32_t colsum_slices(int64_t n) {
-  int64_t s = ceil_div(n, 512);
-  if (s > 64) s = 64;              // few enough partial rows that the fixed-order final sum stays cheap
+  int64_t s = ceil_div(n, 256);
+  if (s > 296) s = 296;            // ~2 CTAs per SM per 32-column strip
   if (s < 1) s = 1;
   return (int32_t)s;
 }

@@ -151,13 +151,22 @@ __global__ void __launch_bounds__(SG_T) k_gemm_simt(SimtGemmParams p) {
   }
 }
 
-// out[i] (+)= sum_z part[z*stride + i]   (fixed order => deterministic)
+// out[i] (+)= sum_z part[z*stride + i].  Fixed association order ((z0+z4+...) + (z1+z5+...) + ...) => deterministic;
+// four independent accumulators keep four loads in flight per thread.
 __global__ void k_reduce_partials(const float* __restrict__ part, int64_t stride, int32_t splits, int64_t n,
                                   float* __restrict__ out, int32_t accumulate) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float s = 0.f;
-  for (int32_t z = 0; z < splits; ++z) s += part[(int64_t)z * stride + i];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int32_t z = 0;
+  for (; z + 3 < splits; z += 4) {
+    s0 += part[(int64_t)z * stride + i];
+    s1 += part[(int64_t)(z + 1) * stride + i];
+    s2 += part[(int64_t)(z + 2) * stride + i];
+    s3 += part[(int64_t)(z + 3) * stride + i];
+  }
+  for (; z < splits; ++z) s0 += part[(int64_t)z * stride + i];
+  const float s = (s0 + s1) + (s2 + s3);
   out[i] = accumulate ? out[i] + s : s;
 }
 
@@ -174,6 +183,14 @@ __global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict_
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (o < O) {
     int64_t i = i0 + ty;
+    for (; i + 56 < i1; i += 64) {      // 8 independent loads in flight per thread
+      const float a0 = __ldg(dy + i * ld + o), a1 = __ldg(dy + (i + 8) * ld + o);
+      const float a2 = __ldg(dy + (i + 16) * ld + o), a3 = __ldg(dy + (i + 24) * ld + o);
+      const float a4 = __ldg(dy + (i + 32) * ld + o), a5 = __ldg(dy + (i + 40) * ld + o);
+      const float a6 = __ldg(dy + (i + 48) * ld + o), a7 = __ldg(dy + (i + 56) * ld + o);
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      s0 += a4; s1 += a5; s2 += a6; s3 += a7;
+    }
     for (; i + 24 < i1; i += 32) {
       s0 += __ldg(dy + i * ld + o);
       s1 += __ldg(dy + (i + 8) * ld + o);

@@ -128,3 +128,31 @@ def test_inference_matches_oracle_layerwise(dev):
         x_all = torch.cat(xs)
     assert out.shape == x_all.shape
     assert rel_err(out, x_all) < 1e-5
+
+
+@pytest.mark.parametrize("name,scale,hidden", [("cora", 1.0, 512), ("pubmed", 0.25, 256), ("arxiv", 0.02, 256),
+                                               ("products", 0.002, 256), ("computers", 0.1, 256)])
+def test_fused_step_on_every_baseline_config_shape(dev, name, scale, hidden):
+    """BASELINE.json configs C1-C5 (feature widths 1433 / 500 / 128 / 100 / 767, the YAML layer counts and fan-outs):
+    one fused step against the untrimmed fp64 oracle on the identical block.  F = 1433 / 767 exercise the scalar
+    aggregation and SIMT GEMM kernels (rows that TMA cannot address), the others the tcgen05 path."""
+    from noise_gnn_b200 import NeighborLoader, SAGE
+    from noise_gnn_b200.synthetic import SHAPES, make_dataset
+    from noise_gnn_b200.train import Trainer
+    sh = SHAPES[name]
+    data, _, train_idx = make_dataset(name, scale=scale, device="cpu", noise_type="sym", noise_rate=0.3)
+    bs = min(sh.batch_size, 128, len(train_idx))
+    loader = NeighborLoader(data, input_nodes=train_idx, num_neighbors=list(sh.fanouts), batch_size=bs, shuffle=True)
+    torch.manual_seed(5)
+    ref = sage_oracle.SAGERef(sh.features, hidden, sh.classes, sh.layers, dropout=0.0, dtype=torch.float64)
+    net = SAGE(sh.features, hidden, sh.classes, sh.layers, dropout=0.0).to(dev)
+    net.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    trainer = Trainer(net)
+    batch = next(iter(loader))
+    tgt = batch.yhn[: batch.batch_size].view(-1).cpu()
+    out_ref = ref(batch.x.cpu().double(), batch.edge_index.cpu())[: batch.batch_size]
+    torch.nn.functional.cross_entropy(out_ref, tgt).backward()
+    logits = trainer.forward_backward(batch, want_logits=True)
+    assert rel_err(logits, out_ref) < 1e-5
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad, q.grad) < 2e-5, (name, k)
