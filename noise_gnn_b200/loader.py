@@ -268,47 +268,60 @@ class NeighborLoader:
             return self._finish_sample(pend)
 
     def __iter__(self):
-        """Yields device-resident batches; block i+1 is sampled on a side stream while the caller trains on block i."""
+        """Yields device-resident batches.  Sampling runs two blocks ahead on a side stream and the backward's CSC
+        transposes on a second one, so the caller's stream only ever sees the step's own kernels; the host blocks
+        only on the 8-int extents of the batch it is about to hand out (sampled long before)."""
         epoch = self.epoch
         self.epoch += 1
         order = self.epoch_permutation(epoch)
-        nb = max(self.num_batches_global, 1)
         steps = len(self)
         with torch.cuda.device(self.device):
             if self.__dict__.get("_side") is None:
                 self._side = torch.cuda.Stream(device=self.device)
-            side = self._side
-
+                self._side_t = torch.cuda.Stream(device=self.device)
+            side, side_t = self._side, self._side_t
             side.wait_stream(torch.cuda.current_stream())          # the resident graph was built on the caller's stream
             order = order.to(self.device) if self.seeds_on_device else order.pin_memory()
+            pending = {}
+            state = {"next": 0}
 
-            def launch(i):
-                g = self.sharder.global_batch_index(i)
-                with torch.cuda.stream(side):
-                    pend = self._launch_sample(self.batch_seeds(order, g), epoch, g)
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                return pend, ev
+            def advance(upto):
+                """Launch sampling for every step < upto that has not been launched yet (idempotent)."""
+                while state["next"] < min(upto, steps):
+                    k = state["next"]
+                    g = self.sharder.global_batch_index(k)
+                    with torch.cuda.stream(side):
+                        pend = self._launch_sample(self.batch_seeds(order, g), epoch, g)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    pending[k] = (pend, ev)
+                    state["next"] = k + 1
 
-            pending = launch(0) if steps > 0 else None
+            advance(2)
             for i in range(steps):
-                pend, ev = pending
+                advance(i + 1)
+                pend, ev = pending.pop(i)
                 ev.synchronize()                                   # host needs the block extents of batch i
                 batch = self._finish_sample(pend)
                 main = torch.cuda.current_stream()
                 if self.transpose_hops > 0:
-                    # the backward's CSC transposes only depend on the block: build them here, off the step's critical
-                    # path (they overlap the previous step still executing on the main stream)
+                    # the backward's CSC transposes only depend on the block: build them off the step's critical path
                     blk = batch.block
-                    with torch.cuda.stream(side):
+                    side_t.wait_event(ev)
+                    with torch.cuda.stream(side_t):
+                        for t in (pend["rowptr"], pend["col"]):
+                            t.record_stream(side_t)
                         for b in range(1, min(self.transpose_hops, len(blk.hop_nodes) - 1) + 1):
                             for t in blk.transpose(blk.hop_edges[b], blk.hop_nodes[b]):
                                 t.record_stream(main)
                         ev = torch.cuda.Event()
-                        ev.record(side)
-                pending = launch(i + 1) if i + 1 < steps else None
+                        ev.record(side_t)
                 main.wait_event(ev)
                 for k in ("seeds", "n_id", "rowptr", "col", "colg", "epos", "counts"):
                     if pend[k] is not None:
                         pend[k].record_stream(main)                # allocated on the side stream, consumed on main
+                # Trainer.train_step calls this right after it has enqueued the step, so the next sampling is queued
+                # while the GPU is busy; a plain consumer gets the same effect when the generator resumes
+                batch._prefetch = lambda upto=i + 3: advance(upto)
                 yield batch
+                advance(i + 3)

@@ -162,6 +162,9 @@ class Trainer:
     def train_step(self, batch, target_attr: str = "yhn", label_attr: Optional[str] = "y", want_logits: bool = False):
         logits = self.forward_backward(batch, target_attr, label_attr, train=True, want_logits=want_logits)
         self.optimizer_step()
+        prefetch = getattr(batch, "_prefetch", None)
+        if prefetch is not None:          # queue the next block's sampling now, while the GPU is busy with this step
+            prefetch()
         return logits
 
     # ------------------------------------------------------------------ autograd variant (same kernels, ~80 FFI calls)
