@@ -249,6 +249,11 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
                        uint64_t drop_seed, uint64_t drop_offset, float* stats /*[2]*/,
                        float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream);
 
+/* 1 (default): inside ngnn_sage_step the weight gradients of layers >= 2 run on an internal auxiliary stream, forked
+ * from / joined back into the caller's stream with events (they are off the backward's critical path); 0: strictly
+ * one stream.                                                                                                  */
+int32_t ngnn_set_step_overlap(int32_t on);
+
 /* In-situ kernel timing for the roofline report: after ngnn_probe_enable(k), the next k ngnn_sage_step calls record
  * a CUDA-event pair on their stream around the layer-1 K-AGG launch; ngnn_probe_read waits for them and returns the
  * per-launch durations in milliseconds.  ngnn_probe_enable(0) disables and frees the events.                         */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "ngnn_sage_step_workspace_bytes": (c_size_t, [_P, c_int32, _P, _P]),
     "ngnn_sage_step": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, c_uint64, c_uint64, _P, _P, c_int64, _P,
                                  c_size_t, _P]),
+    "ngnn_set_step_overlap": (c_int32, [c_int32]),
     "ngnn_probe_enable": (c_int32, [c_int32]),
     "ngnn_probe_read": (c_int32, [_P, c_int32, _P]),
     "ngnn_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P,

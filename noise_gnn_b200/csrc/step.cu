@@ -28,7 +28,7 @@ struct LayerPlan {
 struct StepPlan {
   int L;
   LayerPlan layer[16];
-  size_t dmean, droot, gemm_ws, dgrad_ws, wgrad_ws, sort_ws, ce_rows, total;
+  size_t dmean, droot, gemm_ws, dgrad_ws, wgrad_ws, wgrad_ws_aux, sort_ws, ce_rows, total;
   size_t gemm_ws_bytes, dgrad_ws_bytes, wgrad_ws_bytes, sort_ws_bytes;
   int64_t n_params;
 };
@@ -76,11 +76,26 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
   }
   pl.n_params = (int64_t)poff;
   pl.dmean = take(max_dx); pl.droot = take(max_dx);
-  pl.gemm_ws = take(gws); pl.dgrad_ws = take(dws); pl.wgrad_ws = take(wws); pl.sort_ws = take(sws);
+  pl.gemm_ws = take(gws); pl.dgrad_ws = take(dws); pl.wgrad_ws = take(wws); pl.wgrad_ws_aux = take(wws); pl.sort_ws = take(sws);
   pl.gemm_ws_bytes = gws; pl.dgrad_ws_bytes = dws; pl.wgrad_ws_bytes = wws; pl.sort_ws_bytes = sws;
   pl.ce_rows = take((size_t)max_hop_nodes[0] * 2 * 4);
   pl.total = off + 256;
   return true;
+}
+
+// The weight gradients of layers >= 2 are off the backward's critical path (dY_l -> dgrad -> transpose-sum -> dY_{l-1}):
+// they are forked onto an auxiliary stream (event fork / join, graph-capturable) so their small grids run under the
+// dgrad / K-AGG-T chain instead of after it.
+static cudaStream_t g_aux = nullptr;
+static cudaEvent_t g_fork = nullptr, g_join = nullptr;
+static bool g_use_aux = true;
+
+static int32_t ensure_aux() {
+  if (g_aux != nullptr) return NGNN_OK;
+  NGNN_CUDA(cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking));
+  NGNN_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+  NGNN_CUDA(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+  return NGNN_OK;
 }
 
 // Optional in-situ timing of the layer-1 aggregation launch inside ngnn_sage_step (bench.py's roofline):
@@ -198,14 +213,25 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
   if (!train) return NGNN_OK;
 
   // ---------------- backward ----------------
+  const bool use_aux = g_use_aux && L > 1;
+  if (use_aux) { rc = ensure_aux(); if (rc != NGNN_OK) return rc; }
+  bool aux_used = false;
   for (int i = L - 1; i >= 0; --i) {
     const LayerPlan& lp = pl.layer[i];
     const float* root = i == 0 ? F32(lp.root) : F32(pl.layer[i - 1].out);
     const int64_t ld_root = i == 0 ? lp.F : pl.layer[i - 1].ldo;
     // only the first bs rows of the top layer carry a gradient
     const int64_t n_rows = i == L - 1 ? bs : lp.n_dst;
-    rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
-                         grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
+    if (use_aux && i > 0) {    // fork: dY_i is complete on the main stream here
+      NGNN_CUDA(cudaEventRecord(g_fork, as_stream(stream)));
+      NGNN_CUDA(cudaStreamWaitEvent(g_aux, g_fork, 0));
+      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
+                           grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes, g_aux);
+      aux_used = true;
+    } else {
+      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
+                           grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
+    }
     if (rc != NGNN_OK) return rc;
     if (i == 0) break;   // features are leaves: no data gradient for layer 1
     const LayerPlan& prev = pl.layer[i - 1];
@@ -229,7 +255,13 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
                            F32(prev.out), prev.ldo, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.ldo, stream);
     if (rc != NGNN_OK) return rc;
   }
+  if (aux_used) {            // join: the caller's stream continues only after every weight gradient has landed
+    NGNN_CUDA(cudaEventRecord(g_join, g_aux));
+    NGNN_CUDA(cudaStreamWaitEvent(as_stream(stream), g_join, 0));
+  }
   return NGNN_OK;
 }
+
+int32_t ngnn_set_step_overlap(int32_t on) { g_use_aux = on != 0; return NGNN_OK; }
 
 }  // extern "C"
