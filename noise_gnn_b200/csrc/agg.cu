@@ -37,6 +37,10 @@ struct AggParams {
 
 __device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
+}  // namespace ngnn
+#include "agg_bulk.cuh"   // k_agg_fwd_bulk: rows staged through shared memory by the async copy engines
+namespace ngnn {
+
 // Generic one-row-per-group kernel (all widths, optional add / gate / root gather).  U = neighbour rows in flight.
 template <int G, int VPL, int U>
 __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
@@ -255,6 +259,44 @@ static int g_tune_unroll = 0;    // ngnn_set_tuning(0, u): 0 = default, else for
 static int g_tune_threads = 256; // ngnn_set_tuning(1, t): CTA size 128 / 256 / 512
 static int g_tune_pipe = 1;      // ngnn_set_tuning(3, 0/1): software-pipelined persistent forward kernel
 static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 < F <= 128 (32 / 16 / 8)
+static int g_tune_bulk = 0;      // ngnn_set_tuning(5, v): 0 = off, else 100*mode + 10*chunk_sel + stage_sel (see launch_bulk)
+
+template <int CH, int S, int MODE, bool ROOT>
+static bool launch_bulk_one(const AggParams& p, cudaStream_t st) {
+  const size_t smem = agg_bulk_smem_bytes(CH, S, p.F);
+  if (smem > 227 * 1024) return false;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k_agg_fwd_bulk<CH, S, MODE, ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  int64_t grid = kNumSMs;                                            // persistent: one CTA per SM
+  const int64_t need = ceil_div(p.n_rows, kBulkWarps);
+  if (grid > need) grid = need;
+  k_agg_fwd_bulk<CH, S, MODE, ROOT><<<(unsigned)grid, kBulkWarps * 32, smem, st>>>(p);
+  return true;
+}
+
+// v = 100*(mode+1) + 10*chunk_sel + stages: chunk_sel 0 -> 8 neighbours per unit, 1 -> 16; stages in {3,4,6}
+template <bool ROOT>
+static bool launch_bulk(const AggParams& p, cudaStream_t st, int v) {
+  const int mode = v / 100 - 1, ch = (v / 10) % 10, s = v % 10;
+  if (mode == 0) {
+    if (ch == 0 && s == 4) return launch_bulk_one<8, 4, 0, ROOT>(p, st);
+    if (ch == 0 && s == 6) return launch_bulk_one<8, 6, 0, ROOT>(p, st);
+    if (ch == 1 && s == 3) return launch_bulk_one<16, 3, 0, ROOT>(p, st);
+    if (ch == 1 && s == 4) return launch_bulk_one<16, 4, 0, ROOT>(p, st);
+  } else if (mode == 1) {
+    if (ch == 0 && s == 4) return launch_bulk_one<8, 4, 1, ROOT>(p, st);
+    if (ch == 0 && s == 6) return launch_bulk_one<8, 6, 1, ROOT>(p, st);
+    if (ch == 1 && s == 3) return launch_bulk_one<16, 3, 1, ROOT>(p, st);
+    if (ch == 1 && s == 4) return launch_bulk_one<16, 4, 1, ROOT>(p, st);
+  }
+  return false;
+}
 
 template <int G, int VPL, int U>
 static void launch_v4(const AggParams& p, cudaStream_t st) {
@@ -272,6 +314,10 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
   if (vec) {
     const int64_t F4 = p.F / 4;
     const bool fwd_plain = p.add == nullptr && p.act_ref == nullptr;      // forward aggregation (mean [+ root gather])
+    if (fwd_plain && g_tune_bulk && F4 <= 32 && p.n_rows < (1ll << 31)) {
+      const bool ok = p.root_idx ? launch_bulk<true>(p, st, g_tune_bulk) : launch_bulk<false>(p, st, g_tune_bulk);
+      if (ok) { NGNN_LAUNCH_CHECK(); return NGNN_OK; }
+    }
     if (fwd_plain && g_tune_pipe && F4 > 16 && F4 <= 64) {
       if (F4 <= 32) {
         const int u = g_tune_unroll;
@@ -324,6 +370,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 2 && (value == 32 || value == 16 || value == 8)) { g_tune_group = value; return NGNN_OK; }
   if (key == 3 && (value == 0 || value == 1)) { g_tune_pipe = value; return NGNN_OK; }
   if (key == 4 && (value == 128 || value == 256)) return ngnn_set_gemm_tile(value);
+  if (key == 5 && value >= 0 && value < 300) { g_tune_bulk = value; return NGNN_OK; }
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);
 }
 
