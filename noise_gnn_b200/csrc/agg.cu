@@ -361,6 +361,7 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
 using namespace ngnn;
 
 extern "C" int32_t ngnn_set_gemm_tile(int32_t bn_max);   // gemm.cu
+extern "C" int32_t ngnn_set_gemm_ts(int32_t on);         // gemm.cu
 
 extern "C" {
 
@@ -371,6 +372,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 3 && (value == 0 || value == 1)) { g_tune_pipe = value; return NGNN_OK; }
   if (key == 4 && (value == 128 || value == 256)) return ngnn_set_gemm_tile(value);
   if (key == 5 && value >= 0 && value < 300) { g_tune_bulk = value; return NGNN_OK; }
+  if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);
 }
 

@@ -30,16 +30,17 @@ static int32_t colsum_slices(int64_t n) {
   return (int32_t)s;
 }
 
-}  // namespace ngnn
+int32_t prep_weights_impl(int32_t mode, const float* w_l, const float* w_r, int64_t F, int64_t O, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  if (g_force_simt || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
+  return mode == 0 ? tc_prep_fwd(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, st)
+                   : tc_prep_dgrad(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, st);
+}
 
-using namespace ngnn;
-
-extern "C" {
-
-int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
-                           const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
-                           float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, int32_t* path,
-                           void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l, const float* w_r,
+                      const float* bias, int64_t n, int64_t F, int64_t O, int32_t act, float drop_p, uint64_t seed,
+                      uint64_t offset, float* out, int64_t ld_out, int32_t* path, void* ws, size_t ws_bytes, cudaStream_t st,
+                      bool prepped) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "gemm_fwd: negative size");
   NGNN_REQUIRE(act == NGNN_ACT_NONE || act == NGNN_ACT_RELU, NGNN_E_INVALID, "gemm_fwd: unknown activation %d", act);
   NGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, NGNN_E_INVALID, "gemm_fwd: dropout p=%f outside [0,1)", (double)drop_p);
@@ -50,11 +51,10 @@ int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, in
   NGNN_REQUIRE(a_r == nullptr || w_r != nullptr, NGNN_E_INVALID, "gemm_fwd: a_r without w_r");
   NGNN_REQUIRE(a_l == nullptr || ld_al >= F, NGNN_E_INVALID, "gemm_fwd: ld_al < F");
   NGNN_REQUIRE(a_r == nullptr || ld_ar >= F, NGNN_E_INVALID, "gemm_fwd: ld_ar < F");
-  cudaStream_t st = as_stream(stream);
 
   if (!g_force_simt) {
     int32_t rc = tc_gemm_fwd(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out,
-                             ws, ws_bytes, st);
+                             ws, ws_bytes, st, prepped);
     if (rc == NGNN_OK) { if (path) *path = 1; return NGNN_OK; }
     if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
@@ -68,19 +68,18 @@ int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, in
   return launch_simt_gemm(p, 1, st);
 }
 
-int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
-                        int64_t n, int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root,
-                        int64_t ld_root, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+int32_t dgrad_impl(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr, int64_t n,
+                   int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root, int64_t ld_root, void* ws,
+                   size_t ws_bytes, cudaStream_t st, bool prepped) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "dgrad: negative size");
   if (n == 0 || F == 0) return NGNN_OK;
   NGNN_REQUIRE(dy && ld_dy >= O, NGNN_E_INVALID, "dgrad: bad dy");
   NGNN_REQUIRE(dmean_scaled == nullptr || (w_l && ld_dmean >= F), NGNN_E_INVALID, "dgrad: bad dmean output");
   NGNN_REQUIRE(dx_root == nullptr || (w_r && ld_root >= F), NGNN_E_INVALID, "dgrad: bad dx_root output");
-  cudaStream_t st = as_stream(stream);
   // out[i,f] = sum_o dy[i,o] * W[o,f]  : A = dy (K = O contiguous), B(n=f,k=o) = W[o*F + f]
   if (!g_force_simt) {
     int32_t rc = tc_gemm_dgrad(dy, ld_dy, w_l, w_r, rowptr, n, F, O, dmean_scaled, ld_dmean, dx_root, ld_root, ws,
-                               ws_bytes, st);
+                               ws_bytes, st, prepped);
     if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
   if (dmean_scaled) {
@@ -100,7 +99,29 @@ int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const 
   return NGNN_OK;
 }
 
+}  // namespace ngnn
+
+using namespace ngnn;
+
+extern "C" {
+
+int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
+                           const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
+                           float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, int32_t* path,
+                           void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  return gemm_fwd_impl(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out, path, ws,
+                       ws_bytes, as_stream(stream), false);
+}
+
+int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
+                        int64_t n, int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root,
+                        int64_t ld_root, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  return dgrad_impl(dy, ld_dy, w_l, w_r, rowptr, n, F, O, dmean_scaled, ld_dmean, dx_root, ld_root, ws, ws_bytes,
+                    as_stream(stream), false);
+}
+
 int32_t ngnn_set_gemm_tile(int32_t bn_max) { g_tc_bn_max = bn_max; return NGNN_OK; }   // reached through ngnn_set_tuning(4, .)
+int32_t ngnn_set_gemm_ts(int32_t on) { g_tc_ts = on; return NGNN_OK; }                  // reached through ngnn_set_tuning(6, .)
 
 int32_t ngnn_debug_set_trace(void* device_buffer) {
   g_tc_trace = reinterpret_cast<long long*>(device_buffer);

@@ -170,6 +170,27 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int64_t stride
   out[i] = accumulate ? out[i] + s : s;
 }
 
+// Two independent partial sets reduced by one launch (blockIdx.y selects): dW_l and dW_r of one K-WGRAD call.
+__global__ void k_reduce_partials2(const float* __restrict__ part0, const float* __restrict__ part1, int64_t stride,
+                                   int32_t splits, int64_t n, float* __restrict__ out0, float* __restrict__ out1,
+                                   int32_t accumulate) {
+  const float* part = blockIdx.y == 0 ? part0 : part1;
+  float* out = blockIdx.y == 0 ? out0 : out1;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int32_t z = 0;
+  for (; z + 3 < splits; z += 4) {
+    s0 += part[(int64_t)z * stride + i];
+    s1 += part[(int64_t)(z + 1) * stride + i];
+    s2 += part[(int64_t)(z + 2) * stride + i];
+    s3 += part[(int64_t)(z + 3) * stride + i];
+  }
+  for (; z < splits; ++z) s0 += part[(int64_t)z * stride + i];
+  const float s = (s0 + s1) + (s2 + s3);
+  out[i] = accumulate ? out[i] + s : s;
+}
+
 // column sums of dy over a row slice: part[z*O + o] = sum_{i in slice z} dy[i*ld + o].
 // Block = 32 columns x 8 row lanes: every warp reads 128 contiguous bytes of a row; the 8 row lanes are combined
 // through shared memory in a fixed order (deterministic).

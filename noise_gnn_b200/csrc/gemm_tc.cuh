@@ -89,6 +89,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand read from tensor memory (lane = row, one 32-bit column per tf32 k element): only B crosses the
+// shared-memory port, which the SS form saturates (A 4 KB + B 4 KB per 64-cycle 128x128x8 tf32 MMA = 128 B/cycle).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -229,6 +249,14 @@ constexpr int TG_THREADS = 320;
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// TS = true: the converter warps write A_hi / A_lo into tensor memory (tcgen05.st) and the MMAs take A from there, so a
+// stage holds raw A + B_hi + B_lo only (48 KB at BN = 128 -> 4 stages) and the shared-memory port carries 130 KB per
+// K-block instead of 210 KB (TMA 48 + converter 16 r [+ 32 w] + MMA operands 48 [+ 48] + epilogue 18): the SS form was
+// bound by exactly that port (measured cadence 1550 cycles / K-block = 210 KB / 128 B per cycle).  Needs BN <= 128
+// (TMEM: 2 accumulator buffers + 4 x 64 A columns = 512).
+constexpr uint32_t TS_A_COLS = 64;      // TMEM columns per stage: A_hi [0,32) | A_lo [32,64)
+
+template <bool TS>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
           const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcGemmParams p) {
@@ -237,7 +265,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
 
   const uint32_t a_bytes = TC_BM * TC_BK * 4;                 // 16 KB
   const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 4;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t a_span = TS ? a_bytes : 2 * a_bytes;          // SS keeps a second (lo) plane of A in the stage
+  const uint32_t stage_bytes = a_span + 2 * b_bytes;
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);     // 4 warps x [32][36] floats
   float* bias_s = epi_stage + 4 * EPI_PATCH;                                               // [288]
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(bias_s + 288);
@@ -253,7 +282,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
   const int32_t total_tiles = m_tiles * p.tiles_per_seg * p.num_segs;
   uint32_t buf_cols = 32;
   while (buf_cols < (uint32_t)p.BN) buf_cols <<= 1;
-  const uint32_t tmem_cols = 2 * buf_cols;
+  const uint32_t tmem_cols = TS ? 512u : 2 * buf_cols;
+  const uint32_t tmem_a0 = 2 * buf_cols;                       // TS: first A column
   long long* tr = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
 
@@ -296,8 +326,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
           const int32_t ka = (first ? kb : kb - p.kblocks1) * TC_BK;
           const int32_t kbk = first ? ka : p.b_koff2 + ka;
           tma_load_2d(st, first ? &tmA1 : &tmA2, &full_raw[s], ka, m0);
-          tma_load_2d(st + 2 * a_bytes, &tmBhi, &full_raw[s], kbk, b_row);
-          tma_load_2d(st + 2 * a_bytes + b_bytes, &tmBlo, &full_raw[s], kbk, b_row);
+          tma_load_2d(st + a_span, &tmBhi, &full_raw[s], kbk, b_row);
+          tma_load_2d(st + a_span + b_bytes, &tmBlo, &full_raw[s], kbk, b_row);
         }
       }
     }
@@ -314,19 +344,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1u;
         mbar_wait(&full_conv[s], ph);
+        if (TS) mbar_wait(&full_raw[s], ph);               // B tiles: observed by this thread too (already complete)
         tc_fence_after();
         if (lane == 0) {
           if (tr && it < 32) tr[8 + it * 8 + 3] = clock64();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + 2 * a_bytes, b_lo = b_hi + b_bytes;
+          const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + a_span, b_lo = b_hi + b_bytes;
+          const uint32_t ta = tmem_base + tmem_a0 + (uint32_t)s * TS_A_COLS;
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint32_t koff = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle atom
-            const uint64_t dah = umma_desc_k_sw128(a_hi + koff), dal = umma_desc_k_sw128(a_lo + koff);
             const uint64_t dbh = umma_desc_k_sw128(b_hi + koff), dbl = umma_desc_k_sw128(b_lo + koff);
-            umma_tf32(tmem_d, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_tf32(tmem_d, dal, dbh, idesc, 1u);
-            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            if (TS) {
+              umma_tf32_ts(tmem_d, ta + k * 8, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(tmem_d, ta + 32 + k * 8, dbh, idesc, 1u);
+              umma_tf32_ts(tmem_d, ta + k * 8, dbl, idesc, 1u);
+            } else {
+              const uint64_t dah = umma_desc_k_sw128(a_hi + koff), dal = umma_desc_k_sw128(a_lo + koff);
+              umma_tf32(tmem_d, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);                          // stage reusable once these MMAs have read it
           if (kb == KB - 1) umma_commit(&tmem_full[ab]);   // accumulator complete
@@ -345,18 +383,43 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
         const uint32_t ph = (it / p.stages) & 1u;
         mbar_wait(&full_raw[s], ph);
         if (tr && t == 0 && it < 32) tr[8 + it * 8 + 1] = clock64();
-        float4* hi4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-        float4* lo4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
+        if (TS) {
+          // thread = one tile row (TMEM lane 32*(warp%4) + lane): its 128 swizzled bytes -> hi / lo -> tensor memory
+          const int r = (warp & 3) * 32 + lane;
+          const uint8_t* rowp = smem + (size_t)s * stage_bytes + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tmem_a0 + (uint32_t)s * TS_A_COLS;
 #pragma unroll
-        for (int q4 = 0; q4 < (TC_BM * TC_BK / 4) / 128; ++q4) {
-          const int i = t + 128 * q4;
-          const float4 x = hi4[i];
-          float4 h, l;
-          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-          hi4[i] = h;
-          lo4[i] = l;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = half * 4 + jj;             // 16-byte chunk j of the row sits at chunk position j ^ (r % 8)
+              const float4 x = *reinterpret_cast<const float4*>(rowp + ((j ^ (r & 7)) << 4));
+              float hx, lx;
+              split_tf32(x.x, hx, lx); h[4 * jj + 0] = __float_as_uint(hx); l[4 * jj + 0] = __float_as_uint(lx);
+              split_tf32(x.y, hx, lx); h[4 * jj + 1] = __float_as_uint(hx); l[4 * jj + 1] = __float_as_uint(lx);
+              split_tf32(x.z, hx, lx); h[4 * jj + 2] = __float_as_uint(hx); l[4 * jj + 2] = __float_as_uint(lx);
+              split_tf32(x.w, hx, lx); h[4 * jj + 3] = __float_as_uint(hx); l[4 * jj + 3] = __float_as_uint(lx);
+            }
+            tmem_st16(ta + half * 16, h);
+            tmem_st16(ta + 32 + half * 16, l);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          float4* hi4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+          float4* lo4 = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
+#pragma unroll
+          for (int q4 = 0; q4 < (TC_BM * TC_BK / 4) / 128; ++q4) {
+            const int i = t + 128 * q4;
+            const float4 x = hi4[i];
+            float4 h, l;
+            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+            hi4[i] = h;
+            lo4[i] = l;
+          }
+          fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
         }
-        fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&full_conv[s]);
         if (tr && t == 0 && it < 32) tr[8 + it * 8 + 2] = clock64();
       }
@@ -479,15 +542,19 @@ static inline int32_t round_up_i(int64_t x, int64_t a) { return (int32_t)((x + a
 static int g_tc_bn_max = 128;   // ngnn_set_tuning(4, 128|256): widest N tile.  128 -> 3 smem stages (measured 2x faster
                                 // than 256 -> 2 stages on the products layer-1 shape: TMA latency is the limiter)
 
+static int g_tc_ts = 1;         // ngnn_set_tuning(6, 0|1): A operand from tensor memory (TS form) when BN <= 128
+
 struct TcPlan {
   int32_t BN, tiles_per_seg, stages;
   uint32_t smem_bytes;
+  bool ts;
 };
 static inline TcPlan tc_plan(int64_t n_cols) {
   TcPlan pl;
   pl.BN = n_cols >= g_tc_bn_max ? g_tc_bn_max : round_up_i(n_cols, 16);
   pl.tiles_per_seg = (int32_t)ceil_div(n_cols, pl.BN);
-  const uint32_t stage = 2u * TC_BM * TC_BK * 4u + 2u * (uint32_t)pl.BN * TC_BK * 4u;
+  pl.ts = g_tc_ts != 0 && pl.BN <= 128;
+  const uint32_t stage = (pl.ts ? 1u : 2u) * TC_BM * TC_BK * 4u + 2u * (uint32_t)pl.BN * TC_BK * 4u;
   const uint32_t fixed = 1024u /*align*/ + 4u * EPI_PATCH * 4u /*epilogue staging*/ + 288u * 4u /*bias*/ + 256u /*barriers*/;
   int st = (int)((TC_SMEM_LIMIT - fixed) / stage);
   pl.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
@@ -510,7 +577,8 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
                                 const TcGemmParams& p, const TcPlan& pl, int num_segs, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    NGNN_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    NGNN_CUDA(cudaFuncSetAttribute(k_tc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    NGNN_CUDA(cudaFuncSetAttribute(k_tc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     attr_set = true;
   }
   TcGemmParams pp = p;
@@ -518,17 +586,36 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
   pp.num_segs = num_segs;
   const int64_t tiles = ceil_div(p.M, TC_BM) * pl.tiles_per_seg * num_segs;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);      // persistent: one CTA per SM
-  k_tc_gemm<<<grid, TG_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, pp);
+  if (pl.ts) k_tc_gemm<true><<<grid, TG_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, pp);
+  else k_tc_gemm<false><<<grid, TG_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, pp);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;
 }
 
 // out = drop(act(a_l W_l^T + a_r W_r^T + b)).  Returns NGNN_E_UNSUPPORTED (no error text) when the
 // operands are not TMA-addressable; the caller then uses the SIMT kernel.
+// Packed hi / lo weight planes of the forward projection ([W_l | W_r], K-major) into ws.  `use_l` / `use_r`: which operand
+// pairs the GEMM will contract (a missing one is zero-filled).
+static inline int32_t tc_prep_fwd(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
+                                  size_t ws_bytes, cudaStream_t st) {
+  if (F % 4 != 0 || F < 4 || O < 1) return NGNN_E_UNSUPPORTED;
+  if (ws == nullptr || ws_bytes < tc_fwd_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
+  const int32_t Fpad = round_up_i(F, TC_BK), Kpack = 2 * Fpad;
+  float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  float* lo = hi + align_up((size_t)O * Kpack * sizeof(float), 256) / sizeof(float);
+  PrepParams pp{};
+  pp.w[0] = use_l ? w_l : nullptr; pp.w[1] = use_r ? w_r : nullptr;
+  pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 0; pp.seg_stride = Fpad; pp.Kpack = Kpack; pp.rows_out = (int32_t)O;
+  pp.hi = hi; pp.lo = lo;
+  k_prep_weights<<<(unsigned)ceil_div((int64_t)O * Kpack, 256), 256, 0, st>>>(pp);
+  NGNN_LAUNCH_CHECK();
+  return NGNN_OK;
+}
+
 static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
                                   const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
                                   float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, void* ws,
-                                  size_t ws_bytes, cudaStream_t st) {
+                                  size_t ws_bytes, cudaStream_t st, bool prepped = false) {
   if (F % 4 != 0 || F < 4 || n < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
   if (a_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
   if (a_r && !tma_addressable(a_r, ld_ar)) return NGNN_E_UNSUPPORTED;
@@ -538,12 +625,10 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
   const int32_t Fpad = round_up_i(F, TC_BK), Kpack = 2 * Fpad;
   float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
   float* lo = hi + align_up((size_t)O * Kpack * sizeof(float), 256) / sizeof(float);
-  PrepParams pp{};
-  pp.w[0] = a_l ? w_l : nullptr; pp.w[1] = a_r ? w_r : nullptr;
-  pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 0; pp.seg_stride = Fpad; pp.Kpack = Kpack; pp.rows_out = (int32_t)O;
-  pp.hi = hi; pp.lo = lo;
-  k_prep_weights<<<(unsigned)ceil_div((int64_t)O * Kpack, 256), 256, 0, st>>>(pp);
-  NGNN_LAUNCH_CHECK();
+  if (!prepped) {
+    const int32_t rc = tc_prep_fwd(w_l, w_r, a_l != nullptr, a_r != nullptr, F, O, ws, ws_bytes, st);
+    if (rc != NGNN_OK) return rc;
+  }
 
   const TcPlan pl = tc_plan(O);
   CUtensorMap tA1, tA2, tBh, tBl;
@@ -577,9 +662,27 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
 }
 
 // dmean_scaled = rowscale * (dy W_l), dx_root = dy W_r, both in one launch (two N segments).
+// Packed hi / lo planes of [W_l^T ; W_r^T] (rows = F per segment, K = O) for the data gradient.
+static inline int32_t tc_prep_dgrad(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
+                                    size_t ws_bytes, cudaStream_t st) {
+  if (F < 1 || O < 1) return NGNN_E_UNSUPPORTED;
+  if (ws == nullptr || ws_bytes < tc_dgrad_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
+  const int32_t Kpack = round_up_i(O, TC_BK), Rpad = round_up_i(F, 16);
+  const int32_t rows = 2 * Rpad;
+  float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  float* lo = hi + align_up((size_t)rows * Kpack * sizeof(float), 256) / sizeof(float);
+  PrepParams pp{};
+  pp.w[0] = use_l ? w_l : nullptr; pp.w[1] = use_r ? w_r : nullptr;
+  pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 1; pp.seg_stride = Rpad; pp.Kpack = Kpack; pp.rows_out = rows;
+  pp.hi = hi; pp.lo = lo;
+  k_prep_weights<<<(unsigned)ceil_div((int64_t)rows * Kpack, 256), 256, 0, st>>>(pp);
+  NGNN_LAUNCH_CHECK();
+  return NGNN_OK;
+}
+
 static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
                                     int64_t n, int64_t F, int64_t O, float* dmean, int64_t ld_dmean, float* droot,
-                                    int64_t ld_root, void* ws, size_t ws_bytes, cudaStream_t st) {
+                                    int64_t ld_root, void* ws, size_t ws_bytes, cudaStream_t st, bool prepped = false) {
   if (n < 1 || F < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
   if (!tma_addressable(dy, ld_dy)) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_dgrad_ws_bytes(F, O) || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
@@ -589,12 +692,10 @@ static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float*
   const int32_t rows = 2 * Rpad;
   float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
   float* lo = hi + align_up((size_t)rows * Kpack * sizeof(float), 256) / sizeof(float);
-  PrepParams pp{};
-  pp.w[0] = dmean ? w_l : nullptr; pp.w[1] = droot ? w_r : nullptr;
-  pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 1; pp.seg_stride = Rpad; pp.Kpack = Kpack; pp.rows_out = rows;
-  pp.hi = hi; pp.lo = lo;
-  k_prep_weights<<<(unsigned)ceil_div((int64_t)rows * Kpack, 256), 256, 0, st>>>(pp);
-  NGNN_LAUNCH_CHECK();
+  if (!prepped) {
+    const int32_t rc = tc_prep_dgrad(w_l, w_r, dmean != nullptr, droot != nullptr, F, O, ws, ws_bytes, st);
+    if (rc != NGNN_OK) return rc;
+  }
 
   const TcPlan pl = tc_plan(F);
   CUtensorMap tA, tBh, tBl;
@@ -856,10 +957,10 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
   k_tc_wgrad<<<grid, TC_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
   NGNN_LAUNCH_CHECK();
   if (!direct) {
-    for (int s = 0; s < ns; ++s) {
-      k_reduce_partials<<<(unsigned)ceil_div(O * F, 256), 256, 0, st>>>(parts[s], O * F, pl.splits, O * F, outs[s], accumulate);
-      NGNN_LAUNCH_CHECK();
-    }
+    // same per-element summation order as k_reduce_partials; both weight gradients in one launch
+    dim3 rgrid((unsigned)ceil_div(O * F, 256), (unsigned)ns);
+    k_reduce_partials2<<<rgrid, 256, 0, st>>>(parts[0], parts[ns - 1], O * F, pl.splits, O * F, outs[0], outs[ns - 1], accumulate);
+    NGNN_LAUNCH_CHECK();
   }
   return NGNN_OK;
 }

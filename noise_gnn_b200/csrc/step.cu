@@ -23,6 +23,8 @@ struct LayerPlan {
   size_t off_wl, off_b, off_wr; // element offsets into the flat parameter / gradient buckets
   // arena regions (byte offsets)
   size_t mean, root, out, dy, colptr_t, row_t, perm_t;
+  size_t prep_fwd, prep_dg;     // split weight planes of this layer (forward pack / data-gradient pack)
+  size_t prep_fwd_bytes, prep_dg_bytes;
 };
 
 struct StepPlan {
@@ -71,6 +73,9 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     }
     const size_t g = ngnn_sage_gemm_workspace_bytes(lp.F, lp.O);
     if (g > gws) gws = g;
+    lp.prep_fwd_bytes = g; lp.prep_fwd = take(g);
+    lp.prep_dg_bytes = i > 0 ? ngnn_sage_dgrad_workspace_bytes(lp.F, lp.O) : 0;
+    lp.prep_dg = i > 0 ? take(lp.prep_dg_bytes) : 0;
     const size_t w = ngnn_sage_wgrad_workspace_bytes(lp.n_dst_max, lp.F, lp.O);
     if (w > wws) wws = w;
   }
@@ -87,7 +92,7 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
 // they are forked onto an auxiliary stream (event fork / join, graph-capturable) so their small grids run under the
 // dgrad / K-AGG-T chain instead of after it.
 static cudaStream_t g_aux = nullptr;
-static cudaEvent_t g_fork = nullptr, g_join = nullptr;
+static cudaEvent_t g_fork = nullptr, g_join = nullptr, g_prep = nullptr;
 static bool g_use_aux = true;
 
 static int32_t ensure_aux() {
@@ -95,6 +100,7 @@ static int32_t ensure_aux() {
   NGNN_CUDA(cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking));
   NGNN_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
   NGNN_CUDA(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+  NGNN_CUDA(cudaEventCreateWithFlags(&g_prep, cudaEventDisableTiming));
   return NGNN_OK;
 }
 
@@ -173,6 +179,32 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
   const float p_drop = (train && model->training) ? model->dropout : 0.f;
   int32_t rc;
 
+  // ---------------- split weight planes of every layer, once per step, off the critical path ----------------
+  const bool use_aux = g_use_aux && L > 1;
+  if (use_aux) { rc = ensure_aux(); if (rc != NGNN_OK) return rc; }
+  bool prep_fwd_ok[16], prep_dg_ok[16];
+  {
+    cudaStream_t ps = as_stream(stream);
+    if (use_aux) {             // under the layer-1 aggregation (which does not read the weights)
+      NGNN_CUDA(cudaEventRecord(g_fork, as_stream(stream)));
+      NGNN_CUDA(cudaStreamWaitEvent(g_aux, g_fork, 0));
+      ps = g_aux;
+    }
+    for (int i = 0; i < L; ++i) {
+      const LayerPlan& lp = pl.layer[i];
+      rc = prep_weights_impl(0, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_fwd, lp.prep_fwd_bytes, ps);
+      if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
+      prep_fwd_ok[i] = rc == NGNN_OK;
+      prep_dg_ok[i] = false;
+      if (train && i > 0) {
+        rc = prep_weights_impl(1, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_dg, lp.prep_dg_bytes, ps);
+        if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
+        prep_dg_ok[i] = rc == NGNN_OK;
+      }
+    }
+    if (use_aux) NGNN_CUDA(cudaEventRecord(g_prep, g_aux));
+  }
+
   // ---------------- forward ----------------
   for (int i = 0; i < L; ++i) {
     const LayerPlan& lp = pl.layer[i];
@@ -193,9 +225,11 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
     }
     if (rc != NGNN_OK) return rc;
     const bool last = i == L - 1;
-    rc = ngnn_sage_gemm_fwd(F32(lp.mean), lp.F, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
-                            lp.n_dst, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
-                            drop_offset + (uint64_t)i, F32(lp.out), lp.ldo, nullptr, base + pl.gemm_ws, pl.gemm_ws_bytes, stream);
+    if (i == 0 && use_aux) NGNN_CUDA(cudaStreamWaitEvent(as_stream(stream), g_prep, 0));   // join: weight planes ready
+    rc = gemm_fwd_impl(F32(lp.mean), lp.F, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
+                       lp.n_dst, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
+                       drop_offset + (uint64_t)i, F32(lp.out), lp.ldo, nullptr, base + lp.prep_fwd, lp.prep_fwd_bytes,
+                       as_stream(stream), prep_fwd_ok[i]);
     if (rc != NGNN_OK) return rc;
   }
   const LayerPlan& top = pl.layer[L - 1];
@@ -213,8 +247,6 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
   if (!train) return NGNN_OK;
 
   // ---------------- backward ----------------
-  const bool use_aux = g_use_aux && L > 1;
-  if (use_aux) { rc = ensure_aux(); if (rc != NGNN_OK) return rc; }
   bool aux_used = false;
   for (int i = L - 1; i >= 0; --i) {
     const LayerPlan& lp = pl.layer[i];
@@ -228,6 +260,15 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
       rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
                            grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes, g_aux);
       aux_used = true;
+    } else if (use_aux) {      // layer 1 closes the step: its bias gradient (column sums of dY) runs beside the tensor-core kernel
+      NGNN_CUDA(cudaEventRecord(g_fork, as_stream(stream)));
+      NGNN_CUDA(cudaStreamWaitEvent(g_aux, g_fork, 0));
+      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, nullptr, 0, nullptr, 0, n_rows, lp.F, lp.O, nullptr, nullptr, grads + lp.off_b, 0,
+                           base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes, g_aux);
+      if (rc != NGNN_OK) return rc;
+      aux_used = true;
+      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
+                           grads + lp.off_wr, nullptr, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
     } else {
       rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
                            grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
@@ -236,8 +277,9 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
     if (i == 0) break;   // features are leaves: no data gradient for layer 1
     const LayerPlan& prev = pl.layer[i - 1];
     const int64_t e_lim = i == L - 1 ? block->hop_edges[1 < block->num_hops ? 1 : block->num_hops] : lp.e_lim;
-    rc = ngnn_sage_dgrad(F32(lp.dy), lp.ldo, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows, lp.F, lp.O,
-                         F32(pl.dmean), lp.F, F32(pl.droot), lp.F, base + pl.dgrad_ws, pl.dgrad_ws_bytes, stream);
+    rc = dgrad_impl(F32(lp.dy), lp.ldo, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows, lp.F, lp.O,
+                    F32(pl.dmean), lp.F, F32(pl.droot), lp.F, base + lp.prep_dg, lp.prep_dg_bytes, as_stream(stream),
+                    prep_dg_ok[i]);
     if (rc != NGNN_OK) return rc;
     const int32_t* colptr_t = I32(lp.colptr_t);
     const int32_t* row_t = I32(lp.row_t);
