@@ -31,16 +31,31 @@ struct SimtGemmParams {
   const int32_t* rowptr_scale;  // optional: row m scaled by 1/max(rowptr[m+1]-rowptr[m],1)
 };
 
-// keep-mask of inverted dropout for the 4 columns [4*cq, 4*cq+4) of row m: bit u set => keep
+// Keep-mask of the fused inverted dropout.  One Philox4x32-10 call (128 random bits) serves the 8 columns
+// [8*cg, 8*cg+8) of row m, 16 bits each: column 8*cg + h uses halfword h (word h/2, low half for even h) and is kept
+// iff halfword >= floor(p * 2^16).  (32 bits per element made the tensor-core epilogue spend more instructions on
+// Philox than on everything else; 16 bits resolve p to 1.5e-5.)  oracle/philox.py::dropout_keep_mask restates it.
+__device__ __forceinline__ uint32_t dropout_keep8(uint32_t m, uint32_t cg, uint32_t seed_lo, uint32_t seed_hi,
+                                                  uint32_t off_lo, uint32_t off_hi, uint32_t thr16) {
+  const Philox4 r = philox4x32_10(m, cg, off_lo, off_hi, seed_lo, seed_hi);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t keep = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep |= ((w[i] & 0xFFFFu) >= thr16 ? 1u : 0u) << (2 * i);
+    keep |= ((w[i] >> 16) >= thr16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return keep;
+}
+// the 4 columns [4*cq, 4*cq+4): low or high nibble of the group's 8 bits
 __device__ __forceinline__ uint32_t dropout_keep4(uint32_t m, uint32_t cq, uint32_t seed_lo, uint32_t seed_hi,
-                                                  uint32_t off_lo, uint32_t off_hi, uint32_t thr) {
-  Philox4 r = philox4x32_10(m, cq, off_lo, off_hi, seed_lo, seed_hi);
-  return (r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u);
+                                                  uint32_t off_lo, uint32_t off_hi, uint32_t thr16) {
+  return (dropout_keep8(m, cq >> 1, seed_lo, seed_hi, off_lo, off_hi, thr16) >> ((cq & 1u) * 4u)) & 0xFu;
 }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 65536.0;
   if (t < 0.0) t = 0.0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  if (t > 65535.0) t = 65535.0;
   return (uint32_t)t;
 }
 

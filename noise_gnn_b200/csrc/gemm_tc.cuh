@@ -20,7 +20,7 @@
 // for out-of-bounds rows / columns; stores are bounds-checked.
 #pragma once
 #include "common.cuh"
-#include "gemm_simt.cuh"   // dropout_keep4 / dropout_threshold (the mask definition is shared)
+#include "gemm_simt.cuh"   // dropout_keep8 / dropout_threshold (the mask definition is shared)
 #include <cuda.h>
 
 namespace ngnn {
@@ -98,6 +98,35 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Warp-convergent forms: every lane executes the block, `elect.sync` picks the issuing lane.  Issued from inside an
+// `if (lane == 0)` region the operands are per-thread values and ptxas wraps every UTCHMMA in an ELECT / R2UR / BRA
+// loop (~65 cycles per MMA: as long as the MMA itself, so the tensor pipe never has a backlog and every wait of the
+// issuing thread is a pipe bubble); with warp-uniform operands they go straight to uniform registers.
+__device__ __forceinline__ void umma_tf32_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
 }
 // 16 consecutive 32-bit columns of this thread's TMEM lane <- registers
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -181,6 +210,38 @@ __device__ __forceinline__ void epilogue_store32(float* stage /*warp-private [32
   __syncwarp();
 }
 
+// Same for a 16-column unit, through a [32][20] patch (2.5 KB per warp instead of 4.5 KB: eight epilogue warps fit
+// beside four 48 KB stages); 8 rows x 64 contiguous bytes per store instruction.
+constexpr int EPI16_STRIDE = 20;
+constexpr int EPI16_PATCH = 32 * EPI16_STRIDE;  // floats per warp
+__device__ __forceinline__ void epilogue_store16(float* stage /*warp-private [32][20]*/, const float (&r)[16], float* out,
+                                                 int64_t ld_out, int64_t row0, int64_t n_rows, int32_t nb, int32_t n_cols,
+                                                 bool vec_ok, int lane) {
+  const int sub = lane >> 2, part = lane & 3;          // 8 rows per instruction, 4 lanes (64 B) per row
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<float4*>(stage + lane * EPI16_STRIDE + 4 * g) = make_float4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int rr = 0; rr < 32; rr += 8) {
+    const int lr = rr + sub;
+    const float4 v = *reinterpret_cast<const float4*>(stage + lr * EPI16_STRIDE + 4 * part);
+    const int64_t m = row0 + lr;
+    const int32_t n4 = nb + 4 * part;
+    if (m < n_rows && n4 < n_cols) {
+      float* dst = out + m * ld_out + n4;
+      if (vec_ok && n4 + 3 < n_cols) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) if (n4 + jj < n_cols) dst[jj] = e[jj];
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ----------------------------------------------------------------------------- weight prep
 // Packs up to two [R, C] fp32 weight matrices side by side along K into hi / lo planes [R_out, Kpack]:
 //   transpose == 0: out[r, seg*Cpad + c] = W_seg[r, c]           (forward:  B = [W_l | W_r], rows = O, K = F)
@@ -245,15 +306,21 @@ static long long* g_tc_trace = nullptr;   // ngnn_debug_set_trace
 // (hi/lo split of the A tile in shared memory), warps 6-9 = epilogue.  Two TMEM accumulator buffers let the epilogue
 // of tile j (TMEM -> registers -> smem transpose -> full-line global stores) overlap the main loop of tile j+1; the
 // smem ring runs continuously across tile boundaries.
-constexpr int TG_THREADS = 320;
+constexpr int TG_EPI_WARPS = 8;                  // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int TG_THREADS = 192 + 32 * TG_EPI_WARPS;
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // TS = true: the converter warps write A_hi / A_lo into tensor memory (tcgen05.st) and the MMAs take A from there, so a
 // stage holds raw A + B_hi + B_lo only (48 KB at BN = 128 -> 4 stages) and the shared-memory port carries 130 KB per
 // K-block instead of 210 KB (TMA 48 + converter 16 r [+ 32 w] + MMA operands 48 [+ 48] + epilogue 18): the SS form was
 // bound by exactly that port (measured cadence 1550 cycles / K-block = 210 KB / 128 B per cycle).  Needs BN <= 128
 // (TMEM: 2 accumulator buffers + 4 x 64 A columns = 512).
+// ring position without a runtime modulo / division per K-block
+struct StageIter {
+  int s; uint32_t ph; int n;
+  __device__ __forceinline__ void next() { if (++s == n) { s = 0; ph ^= 1u; } }
+};
 constexpr uint32_t TS_A_COLS = 64;      // TMEM columns per stage: A_hi [0,32) | A_lo [32,64)
 
 template <bool TS>
@@ -267,8 +334,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
   const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 4;
   const uint32_t a_span = TS ? a_bytes : 2 * a_bytes;          // SS keeps a second (lo) plane of A in the stage
   const uint32_t stage_bytes = a_span + 2 * b_bytes;
-  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);     // 4 warps x [32][36] floats
-  float* bias_s = epi_stage + 4 * EPI_PATCH;                                               // [288]
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);     // 8 warps x [32][20] floats
+  float* bias_s = epi_stage + TG_EPI_WARPS * EPI16_PATCH;                                  // [288]
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(bias_s + 288);
   uint64_t* full_conv = full_raw + TC_MAX_STAGES;
   uint64_t* empty = full_conv + TC_MAX_STAGES;
@@ -289,8 +356,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 128); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    // full_raw: the raw A tile landed (converters wait); full_conv: 128 converter arrivals + the producer's arrival
+    // carrying the B tiles' bytes (the MMA thread waits on this one only)
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 129); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * TG_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -311,76 +380,78 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
+      StageIter si{0, 0u, p.stages};
       for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int32_t m0, seg_id, n0;
         decode(tile, m0, seg_id, n0);
         const int32_t b_row = p.seg[seg_id].b_row0 + n0;
-        for (int32_t kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
+        for (int32_t kb = 0; kb < KB; ++kb, ++it, si.next()) {
+          const int s = si.s;
+          const uint32_t ph = si.ph;
           mbar_wait(&empty[s], ph ^ 1u);
           if (tr && it < 32) tr[8 + it * 8 + 0] = clock64();
           uint8_t* st = smem + (size_t)s * stage_bytes;
-          mbar_arrive_expect_tx(&full_raw[s], a_bytes + 2 * b_bytes);
+          mbar_arrive_expect_tx(&full_raw[s], a_bytes);
+          mbar_arrive_expect_tx(&full_conv[s], 2 * b_bytes);
           const bool first = kb < p.kblocks1;
           const int32_t ka = (first ? kb : kb - p.kblocks1) * TC_BK;
           const int32_t kbk = first ? ka : p.b_koff2 + ka;
           tma_load_2d(st, first ? &tmA1 : &tmA2, &full_raw[s], ka, m0);
-          tma_load_2d(st + a_span, &tmBhi, &full_raw[s], kbk, b_row);
-          tma_load_2d(st + a_span + b_bytes, &tmBlo, &full_raw[s], kbk, b_row);
+          tma_load_2d(st + a_span, &tmBhi, &full_conv[s], kbk, b_row);
+          tma_load_2d(st + a_span + b_bytes, &tmBlo, &full_conv[s], kbk, b_row);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The whole warp runs the loop in convergence (warp-uniform operands, see umma_tf32_elect); ONE barrier wait per
+    // K-block: the B tiles complete_tx on full_conv too, so its phase means "B landed and A converted".
     const uint32_t idesc = umma_idesc_tf32(TC_BM, (uint32_t)p.BN);
     uint32_t it = 0, j = 0;
+    StageIter si{0, 0u, p.stages};
     for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const uint32_t ab = j & 1u;
       mbar_wait(&tmem_empty[ab], ((j >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + ab * buf_cols;
-      for (int32_t kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1u;
+      for (int32_t kb = 0; kb < KB; ++kb, ++it, si.next()) {
+        const int s = si.s;
+        const uint32_t ph = si.ph;
         mbar_wait(&full_conv[s], ph);
-        if (TS) mbar_wait(&full_raw[s], ph);               // B tiles: observed by this thread too (already complete)
         tc_fence_after();
-        if (lane == 0) {
-          if (tr && it < 32) tr[8 + it * 8 + 3] = clock64();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + a_span, b_lo = b_hi + b_bytes;
-          const uint32_t ta = tmem_base + tmem_a0 + (uint32_t)s * TS_A_COLS;
+        if (tr && lane == 0 && it < 32) tr[8 + it * 8 + 3] = clock64();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + a_span, b_lo = b_hi + b_bytes;
+        const uint32_t ta = tmem_base + tmem_a0 + (uint32_t)s * TS_A_COLS;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint32_t koff = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle atom
-            const uint64_t dbh = umma_desc_k_sw128(b_hi + koff), dbl = umma_desc_k_sw128(b_lo + koff);
-            if (TS) {
-              umma_tf32_ts(tmem_d, ta + k * 8, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32_ts(tmem_d, ta + 32 + k * 8, dbh, idesc, 1u);
-              umma_tf32_ts(tmem_d, ta + k * 8, dbl, idesc, 1u);
-            } else {
-              const uint64_t dah = umma_desc_k_sw128(a_hi + koff), dal = umma_desc_k_sw128(a_lo + koff);
-              umma_tf32(tmem_d, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_tf32(tmem_d, dal, dbh, idesc, 1u);
-              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-            }
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint32_t koff = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle atom
+          const uint64_t dbh = umma_desc_k_sw128(b_hi + koff), dbl = umma_desc_k_sw128(b_lo + koff);
+          if (TS) {
+            umma_tf32_ts_elect(tmem_d, ta + k * 8, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_ts_elect(tmem_d, ta + 32 + k * 8, dbh, idesc, 1u);
+            umma_tf32_ts_elect(tmem_d, ta + k * 8, dbl, idesc, 1u);
+          } else {
+            const uint64_t dah = umma_desc_k_sw128(a_hi + koff), dal = umma_desc_k_sw128(a_lo + koff);
+            umma_tf32_elect(tmem_d, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_elect(tmem_d, dal, dbh, idesc, 1u);
+            umma_tf32_elect(tmem_d, dah, dbl, idesc, 1u);
           }
-          umma_commit(&empty[s]);                          // stage reusable once these MMAs have read it
-          if (kb == KB - 1) umma_commit(&tmem_full[ab]);   // accumulator complete
-          if (tr && it < 32) tr[8 + it * 8 + 4] = clock64();
         }
-        __syncwarp();
+        if (tr && lane == 0 && it < 32) tr[8 + it * 8 + 4] = clock64();
+        umma_commit_elect(&empty[s]);                          // stage reusable once these MMAs have read it
+        if (kb == KB - 1) umma_commit_elect(&tmem_full[ab]);   // accumulator complete
       }
     }
   } else if (warp < 6) {
     // ===================== converter warps (2..5) =====================
     const int t = threadIdx.x - 64;                  // 0..127
     uint32_t it = 0;
+    StageIter si{0, 0u, p.stages};
     for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int32_t kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1u;
+      for (int32_t kb = 0; kb < KB; ++kb, ++it, si.next()) {
+        const int s = si.s;
+        const uint32_t ph = si.ph;
         mbar_wait(&full_raw[s], ph);
         if (tr && t == 0 && it < 32) tr[8 + it * 8 + 1] = clock64();
         if (TS) {
@@ -425,12 +496,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
       }
     }
   } else {
-    // ===================== epilogue warps (6..9) =====================
-    const int et = threadIdx.x - 192;                // 0..127
+    // ===================== epilogue warps (6..13) =====================
+    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31); the pair alternates the tile's
+    // 32-column chunks.  One warp per scheduler could not hide its own latencies (Philox chains, tcgen05.ld, smem
+    // transpose): ncu showed the epilogue as long as the main loop it is supposed to hide under.
+    const int et = threadIdx.x - 192;                // 0..255
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    float* stage = epi_stage + (warp - 6) * EPI_PATCH;
+    const int half = (warp - 6) >> 2;                // which chunks of the tile: (c / 32) % 2 == half
+    float* stage = epi_stage + (warp - 6) * EPI16_PATCH;
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    // last chunk this warp reads from TMEM (-1: none — it hands the buffer back right away)
+    int32_t last_c = -1;
+    for (int32_t c = 32 * half; c < p.BN; c += 64) last_c = c;
     uint32_t j = 0;
     for (int32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       int32_t m0, seg_id, n0;
@@ -439,7 +517,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
       const uint32_t ab = j & 1u;
       // bias of this tile's columns -> smem (the previous tile's readers are past their last use: barrier first)
       epi_bar_sync();
-      for (int i = et; i < 288; i += 128) bias_s[i] = (p.bias != nullptr && n0 + i < sg.n_cols) ? __ldg(p.bias + n0 + i) : 0.f;
+      for (int i = et; i < 288; i += 32 * TG_EPI_WARPS) bias_s[i] = (p.bias != nullptr && n0 + i < sg.n_cols) ? __ldg(p.bias + n0 + i) : 0.f;
       epi_bar_sync();
       const int64_t row0 = (int64_t)m0 + q * 32;
       const int64_t m = row0 + lane;
@@ -451,44 +529,44 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
       mbar_wait(&tmem_full[ab], (j >> 1) & 1u);
       tc_fence_after();
       if (tr && et == 0 && j == 0) tr[1] = clock64();
+      if (last_c < 0) { tc_fence_before(); mbar_arrive(&tmem_empty[ab]); }
       const uint32_t tmem_d = tmem_base + ab * buf_cols + ((uint32_t)(q * 32) << 16);
-      for (int32_t c = 0; c < p.BN; c += 32) {
-        const int32_t nb = n0 + c;
-        const bool live = nb < sg.n_cols;            // warp-uniform
-        uint32_t v[32];
-        if (live) {
-          uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
-          uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
-          tmem_ld16(tmem_d + (uint32_t)c, v0);
-          if (c + 16 < p.BN) tmem_ld16(tmem_d + (uint32_t)(c + 16), v1);
-          else {
+      for (int32_t c = 32 * half; c < p.BN; c += 64) {
+        // a 32-column chunk as two 16-column units (16 accumulator + 16 result registers live at a time: the kernel
+        // runs 448 threads, 128 registers each)
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) v1[jj] = 0u;
+        for (int h = 0; h < 2; ++h) {
+          const int32_t cc = c + 16 * h;
+          const int32_t nb = n0 + cc;
+          const bool live = cc < p.BN && nb < sg.n_cols;         // warp-uniform
+          uint32_t v[16];
+          if (live) tmem_ld16(tmem_d + (uint32_t)cc, v);
+          if (c == last_c && h == 1) {                            // this warp's last TMEM read of the tile: hand the buffer back
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[ab]);
           }
-        }
-        if (c + 32 >= p.BN) {                          // last TMEM read of this tile done: hand the buffer back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[ab]);
-        }
-        if (!live) continue;
-        float r[32];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int32_t n4 = nb + 4 * g;
-          uint32_t keep = 0xFu;
-          if (p.drop_p > 0.f && row_ok && n4 < sg.n_cols)
-            keep = dropout_keep4((uint32_t)m, (uint32_t)(n4 >> 2), p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr);
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * g);     // smem broadcast
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            float x = (__uint_as_float(v[4 * g + jj]) + bb[jj]) * rs;
-            if (p.act == NGNN_ACT_RELU) x = fmaxf(x, 0.f);
-            if (p.drop_p > 0.f) x = ((keep >> jj) & 1u) ? x * keep_scale : 0.f;
-            r[4 * g + jj] = x;
+          if (!live) continue;
+          uint32_t keep16 = 0xFFFFu;                              // nb is a multiple of 16: two 8-column Philox groups
+          if (p.drop_p > 0.f && row_ok) {
+            keep16 = dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3), p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr);
+            if (nb + 8 < sg.n_cols)
+              keep16 |= dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3) + 1u, p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr) << 8;
           }
+          float r[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + 4 * g);     // smem broadcast
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float x = (__uint_as_float(v[4 * g + jj]) + bb[jj]) * rs;
+              if (p.act == NGNN_ACT_RELU) x = fmaxf(x, 0.f);
+              if (p.drop_p > 0.f) x = ((keep16 >> (4 * g + jj)) & 1u) ? x * keep_scale : 0.f;
+              r[4 * g + jj] = x;
+            }
+          }
+          epilogue_store16(stage, r, sg.out, sg.ld_out, row0, p.M, nb, sg.n_cols, vec_ok, lane);
         }
-        epilogue_store32(stage, r, sg.out, sg.ld_out, row0, p.M, nb, sg.n_cols, vec_ok, lane);
       }
       if (tr && et == 0 && j == 0) tr[3] = clock64();
     }
@@ -555,7 +633,7 @@ static inline TcPlan tc_plan(int64_t n_cols) {
   pl.tiles_per_seg = (int32_t)ceil_div(n_cols, pl.BN);
   pl.ts = g_tc_ts != 0 && pl.BN <= 128;
   const uint32_t stage = (pl.ts ? 1u : 2u) * TC_BM * TC_BK * 4u + 2u * (uint32_t)pl.BN * TC_BK * 4u;
-  const uint32_t fixed = 1024u /*align*/ + 4u * EPI_PATCH * 4u /*epilogue staging*/ + 288u * 4u /*bias*/ + 256u /*barriers*/;
+  const uint32_t fixed = 1024u /*align*/ + (uint32_t)TG_EPI_WARPS * EPI16_PATCH * 4u /*epilogue staging*/ + 288u * 4u /*bias*/ + 256u /*barriers*/;
   int st = (int)((TC_SMEM_LIMIT - fixed) / stage);
   pl.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
   pl.smem_bytes = (uint32_t)pl.stages * stage + fixed;

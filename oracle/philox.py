@@ -34,14 +34,17 @@ def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
 
 
 def dropout_keep_mask(n_rows: int, n_cols: int, p: float, seed: int, offset: int) -> np.ndarray:
-    """Keep-mask of the fused dropout in K-GEMM's epilogue (noise_gnn_b200/csrc/gemm_simt.cuh):
-    element (m, c) is kept iff word[c % 4] of philox(counter=(m, c//4, offset_lo, offset_hi),
-    key=(seed_lo, seed_hi)) >= floor(p * 2^32)."""
-    thr = min(max(int(p * 4294967296.0), 0), 4294967295)
-    cq = (n_cols + 3) // 4
+    """Keep-mask of the fused dropout in K-GEMM's epilogue (noise_gnn_b200/csrc/gemm_simt.cuh::dropout_keep8):
+    one philox(counter=(m, c//8, offset_lo, offset_hi), key=(seed_lo, seed_hi)) call serves 8 columns with 16 bits
+    each; element (m, c) uses halfword h = c % 8 (word h//2, low half for even h) and is kept iff it is
+    >= floor(p * 2^16)."""
+    thr = min(max(int(p * 65536.0), 0), 65535)
+    cg = (n_cols + 7) // 8
     m = np.arange(n_rows, dtype=np.uint64)[:, None]
-    q = np.arange(cq, dtype=np.uint64)[None, :]
-    words = philox4x32_10(m, q, offset & 0xFFFFFFFF, (offset >> 32) & 0xFFFFFFFF,
+    g = np.arange(cg, dtype=np.uint64)[None, :]
+    words = philox4x32_10(m, g, offset & 0xFFFFFFFF, (offset >> 32) & 0xFFFFFFFF,
                           seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    w = np.stack(words, axis=-1).reshape(n_rows, cq * 4)[:, :n_cols]
-    return w >= np.uint32(thr)
+    w = np.stack(words, axis=-1)                                   # [rows, groups, 4 words]
+    halves = np.stack([w & np.uint32(0xFFFF), w >> np.uint32(16)], axis=-1)   # [rows, groups, 4, (low, high)]
+    h = halves.reshape(n_rows, cg * 8)[:, :n_cols]
+    return h >= np.uint32(thr)

@@ -10,9 +10,10 @@ from noise_gnn_b200 import _lib, ops  # noqa: E402
 
 dev = torch.device("cuda", 0)
 import itertools
-for bn, (n, F, O) in itertools.product((256, 128), ((77000, 100, 256), (8200, 256, 256))):
+for (bn, ts), (n, F, O) in itertools.product(((128, 1),), ((77000, 100, 256),)):
     _lib.call('ngnn_set_tuning', 4, bn)
-    print('BN_max', bn)
+    _lib.call('ngnn_set_tuning', 6, ts)
+    print('BN_max', bn, 'A-in-TMEM' if ts else 'A-in-smem')
     a_l, a_r = torch.randn(n, F, device=dev), torch.randn(n, F, device=dev)
     w_l, w_r, b = torch.randn(O, F, device=dev), torch.randn(O, F, device=dev), torch.randn(O, device=dev)
     for _ in range(3):
@@ -29,7 +30,7 @@ for bn, (n, F, O) in itertools.product((256, 128), ((77000, 100, 256), (8200, 25
     t0 = t[0]
     kb = 2 * ((F + 31) // 32)
     print(f"n={n} F={F} O={O}: kernel+prep {s.elapsed_time(e) * 1e3:.1f} us; CTA0: tmem_full at {t[1] - t0} cyc, epilogue done at {t[3] - t0} cyc, {kb} K-blocks")
-    print("  kb: producer_go  raw_landed  conv_done  mma_start  mma_issued   (cycles since CTA start)")
-    for k in range(min(32, kb * 4)):
-        r = t[8 + 8 * k: 8 + 8 * k + 5]
+    print("  kb: producer_go  raw_landed  conv_done  mma_start  mma_issued  committed  wait1_done  loop_top   (cycles since CTA start)")
+    for k in range(min(24, kb * 3)):
+        r = t[8 + 8 * k: 8 + 8 * k + 8]
         print(f"  {k:2d}: " + "  ".join(f"{v - t0:9d}" for v in r))

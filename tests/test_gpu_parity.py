@@ -167,13 +167,16 @@ GEMM_SHAPES = [(1, 4, 3), (130, 100, 256), (700, 256, 47), (257, 128, 40), (300,
                (1000, 500, 3), (513, 256, 256), (64, 512, 7), (300, 64, 512), (4000, 100, 256)]
 
 
-@pytest.fixture(params=["auto", "simt"])
+@pytest.fixture(params=["auto", "ss", "simt"])
 def gemm_path(request, dev):
-    """Runs a GEMM test twice: automatic dispatch (tcgen05 where the operands are TMA-addressable) and forced SIMT."""
+    """Runs a GEMM test three times: automatic dispatch (tcgen05 where the operands are TMA-addressable; A operand in
+    tensor memory), tcgen05 with both operands in shared memory ("ss"), and forced SIMT."""
     from noise_gnn_b200 import _lib
     _lib.call("ngnn_set_gemm_path", 1 if request.param == "simt" else 0)
-    yield request.param
+    _lib.call("ngnn_set_tuning", 6, 0 if request.param == "ss" else 1)
+    yield "auto" if request.param == "ss" else request.param
     _lib.call("ngnn_set_gemm_path", 0)
+    _lib.call("ngnn_set_tuning", 6, 1)
 
 
 @pytest.mark.parametrize("n,F,O", GEMM_SHAPES)
