@@ -830,6 +830,10 @@ struct TcWgradParams {
   TcWgradSeg seg[2];
 };
 
+// TS = true: dY^T (the M x K operand) is transposed + split by the converter warps straight into tensor memory
+// (lane = output row o, column = reduction row i), X stays in shared memory (MN-major, split in place): the SS form
+// moved 218 KB per K-block through the 128 B/cycle shared-memory port for 711 cycles of tensor work.
+template <bool TS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX1,
            const __grid_constant__ CUtensorMap tmX2, const TcWgradParams p) {
@@ -838,7 +842,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
 
   const uint32_t a_bytes = 4 * TW_BOX_BYTES;                   // 128 o-columns: 16 KB
   const uint32_t b_bytes = (uint32_t)p.nbox * TW_BOX_BYTES;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t a_span = TS ? a_bytes : 2 * a_bytes;
+  const uint32_t stage_bytes = a_span + 2 * b_bytes;
   uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* full_conv = full_raw + TC_MAX_STAGES;
@@ -855,8 +860,9 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
   const int32_t kb_beg = blockIdx.z * p.kblocks_per_split;
   const int32_t kb_end = min(p.kblocks_total, kb_beg + p.kblocks_per_split);
   const int32_t KB = max(kb_end - kb_beg, 0);
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+  uint32_t acc_cols = 32;
+  while (acc_cols < (uint32_t)p.BN) acc_cols <<= 1;
+  const uint32_t tmem_cols = TS ? 512u : acc_cols;             // TS: accumulator (<= 256) + 4 x 64 A columns
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmX2);
@@ -873,60 +879,103 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
   if (warp == 0) {
     if (lane == 0) {
       const CUtensorMap* tmX = sg.use_x2 ? &tmX2 : &tmX1;
-      for (int32_t it = 0; it < KB; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      StageIter si{0, 0u, p.stages};
+      for (int32_t it = 0; it < KB; ++it, si.next()) {
+        const int s = si.s;
+        const uint32_t ph = si.ph;
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_raw[s], a_bytes + b_bytes);
         const int32_t i0 = (kb_beg + it) * TW_KB;
 #pragma unroll
         for (int g = 0; g < 4; ++g) tma_load_2d(st + g * TW_BOX_BYTES, &tmDY, &full_raw[s], o0 + 32 * g, i0);
-        for (int g = 0; g < p.nbox; ++g) tma_load_2d(st + 2 * a_bytes + g * TW_BOX_BYTES, tmX, &full_raw[s], f0 + 32 * g, i0);
+        for (int g = 0; g < p.nbox; ++g) tma_load_2d(st + a_span + g * TW_BOX_BYTES, tmX, &full_raw[s], f0 + 32 * g, i0);
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_tf32(TC_BM, (uint32_t)p.BN, 1, 1);   // both operands MN-major
-    for (int32_t it = 0; it < KB; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-      mbar_wait(&full_conv[s], ph);
+    // whole warp in convergence, elect-issued MMAs (warp-uniform operands: see umma_tf32_elect)
+    const uint32_t idesc = umma_idesc_tf32(TC_BM, (uint32_t)p.BN, TS ? 0 : 1, 1);   // SS: both operands MN-major; TS: A K-major in TMEM
+    StageIter si{0, 0u, p.stages};
+    for (int32_t it = 0; it < KB; ++it, si.next()) {
+      const int s = si.s;
+      mbar_wait(&full_conv[s], si.ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + 2 * a_bytes, b_lo = b_hi + b_bytes;
+      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + a_span, b_lo = b_hi + b_bytes;
+      const uint32_t ta = tmem_base + acc_cols + (uint32_t)s * TS_A_COLS;
 #pragma unroll
-        for (int k = 0; k < TW_KB / 8; ++k) {
-          const uint32_t koff = k * 1024;   // 8 reduction rows x 128 B
+      for (int k = 0; k < TW_KB / 8; ++k) {
+        const uint32_t koff = k * 1024;   // 8 reduction rows x 128 B
+        const uint64_t dbh = umma_desc_mn_sw128(b_hi + koff, TW_BOX_BYTES, 512), dbl = umma_desc_mn_sw128(b_lo + koff, TW_BOX_BYTES, 512);
+        if (TS) {
+          umma_tf32_ts_elect(tmem_base, ta + k * 8, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_tf32_ts_elect(tmem_base, ta + 32 + k * 8, dbh, idesc, 1u);
+          umma_tf32_ts_elect(tmem_base, ta + k * 8, dbl, idesc, 1u);
+        } else {
           const uint64_t dah = umma_desc_mn_sw128(a_hi + koff, TW_BOX_BYTES, 512), dal = umma_desc_mn_sw128(a_lo + koff, TW_BOX_BYTES, 512);
-          const uint64_t dbh = umma_desc_mn_sw128(b_hi + koff, TW_BOX_BYTES, 512), dbl = umma_desc_mn_sw128(b_lo + koff, TW_BOX_BYTES, 512);
-          umma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32_elect(tmem_base, dah, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_tf32_elect(tmem_base, dal, dbh, idesc, 1u);
+          umma_tf32_elect(tmem_base, dah, dbl, idesc, 1u);
         }
-        umma_commit(&empty[s]);
-        if (it == KB - 1) umma_commit(tmem_full);
       }
-      __syncwarp();
+      umma_commit_elect(&empty[s]);
+      if (it == KB - 1) umma_commit_elect(tmem_full);
     }
   } else {
     const int t = threadIdx.x - 64;
     const int n4 = (int)((a_bytes + b_bytes) / 16);            // float4s to split per stage (A then B, hi planes)
-    for (int32_t it = 0; it < KB; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+    StageIter si{0, 0u, p.stages};
+    for (int32_t it = 0; it < KB; ++it, si.next()) {
+      const int s = si.s;
+      const uint32_t ph = si.ph;
       mbar_wait(&full_raw[s], ph);
       uint8_t* st = smem + (size_t)s * stage_bytes;
-      const int a4 = (int)(a_bytes / 16);
-      for (int i = t; i < n4; i += 128) {
-        float4* hp; float4* lp;
-        if (i < a4) { hp = reinterpret_cast<float4*>(st) + i; lp = reinterpret_cast<float4*>(st + a_bytes) + i; }
-        else { hp = reinterpret_cast<float4*>(st + 2 * a_bytes) + (i - a4); lp = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes) + (i - a4); }
-        const float4 x = *hp;
-        float4 h, l;
-        split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-        *hp = h;
-        *lp = l;
+      if (TS) {
+        // A: thread = output row o = 32*(warp%4) + lane = column `lane` of box (warp%4); reduction row i of that box is one
+        // 128-byte line whose 32-byte chunks are XOR-ed with (i % 4) (SWIZZLE_128B_ATOM_32B) -> a warp reads one full
+        // line per i, conflict-free.  32 values -> hi / lo -> 64 TMEM columns of this thread's lane.
+        const int qa = warp & 3;
+        const float* box = reinterpret_cast<const float*>(st + (size_t)qa * TW_BOX_BYTES);
+        const uint32_t ta = tmem_base + ((uint32_t)(qa * 32) << 16) + acc_cols + (uint32_t)s * TS_A_COLS;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t h[16], l[16];
+#pragma unroll
+          for (int ii = 0; ii < 16; ++ii) {
+            const int i = half * 16 + ii;
+            const float x = box[i * 32 + ((((lane >> 3) ^ (i & 3)) << 3) | (lane & 7))];
+            float hx, lx;
+            split_tf32(x, hx, lx);
+            h[ii] = __float_as_uint(hx); l[ii] = __float_as_uint(lx);
+          }
+          tmem_st16(ta + half * 16, h);
+          tmem_st16(ta + 32 + half * 16, l);
+        }
+        // B: split in place (hi) + lo plane
+        float4* bh = reinterpret_cast<float4*>(st + a_span);
+        float4* bl = reinterpret_cast<float4*>(st + a_span + b_bytes);
+        const int b4 = (int)(b_bytes / 16);
+        for (int i = t; i < b4; i += 128) {
+          const float4 x = bh[i];
+          float4 h, l;
+          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+          bh[i] = h;
+          bl[i] = l;
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        const int a4 = (int)(a_bytes / 16);
+        for (int i = t; i < n4; i += 128) {
+          float4* hp; float4* lp;
+          if (i < a4) { hp = reinterpret_cast<float4*>(st) + i; lp = reinterpret_cast<float4*>(st + a_bytes) + i; }
+          else { hp = reinterpret_cast<float4*>(st + 2 * a_bytes) + (i - a4); lp = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes) + (i - a4); }
+          const float4 x = *hp;
+          float4 h, l;
+          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+          *hp = h;
+          *lp = l;
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(&full_conv[s]);
@@ -966,13 +1015,15 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
 struct TcWgradPlan {
   int32_t BN, nbox, tiles_per_seg, stages, splits, kblocks_total, kblocks_per_split;
   uint32_t smem_bytes;
+  bool ts;
 };
 static inline TcWgradPlan tc_wgrad_plan(int64_t n, int64_t F, int64_t O, int num_segs) {
   TcWgradPlan pl;
   pl.BN = F >= 256 ? 256 : round_up_i(F, 16);
   pl.nbox = (pl.BN + 31) / 32;
   pl.tiles_per_seg = (int32_t)ceil_div(F, pl.BN);
-  const uint32_t stage = 2u * 4u * TW_BOX_BYTES + 2u * (uint32_t)pl.nbox * TW_BOX_BYTES;
+  pl.ts = g_tc_ts != 0;
+  const uint32_t stage = (pl.ts ? 1u : 2u) * 4u * TW_BOX_BYTES + 2u * (uint32_t)pl.nbox * TW_BOX_BYTES;
   int st = (int)((TC_SMEM_LIMIT - 2048u) / stage);
   pl.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
   pl.smem_bytes = (uint32_t)pl.stages * stage + 1024u + 256u;
@@ -1028,11 +1079,13 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
 
   static bool attr_set = false;
   if (!attr_set) {
-    NGNN_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    NGNN_CUDA(cudaFuncSetAttribute(k_tc_wgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    NGNN_CUDA(cudaFuncSetAttribute(k_tc_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(O, TC_BM), (unsigned)(pl.tiles_per_seg * ns), (unsigned)pl.splits);
-  k_tc_wgrad<<<grid, TC_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
+  if (pl.ts) k_tc_wgrad<true><<<grid, TC_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
+  else k_tc_wgrad<false><<<grid, TC_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
   NGNN_LAUNCH_CHECK();
   if (!direct) {
     // same per-element summation order as k_reduce_partials; both weight gradients in one launch
