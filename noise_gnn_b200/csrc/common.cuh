@@ -52,6 +52,10 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 // Returns NGNN_E_UNSUPPORTED when the shape takes the SIMT kernels (which read the weights directly).
 int32_t prep_weights_impl(int32_t mode, const float* w_l, const float* w_r, int64_t F, int64_t O, void* ws, size_t ws_bytes,
                           cudaStream_t st);
+// Batched form: prep_batch_add collects jobs (same arguments / return codes), prep_batch_launch runs them in one launch.
+void prep_batch_begin();
+int32_t prep_batch_add(int32_t mode, const float* w_l, const float* w_r, int64_t F, int64_t O, void* ws, size_t ws_bytes);
+int32_t prep_batch_launch(cudaStream_t st);
 int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l, const float* w_r,
                       const float* bias, int64_t n, int64_t F, int64_t O, int32_t act, float drop_p, uint64_t seed,
                       uint64_t offset, float* out, int64_t ld_out, int32_t* path, void* ws, size_t ws_bytes, cudaStream_t st,

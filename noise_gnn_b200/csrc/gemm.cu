@@ -37,6 +37,32 @@ int32_t prep_weights_impl(int32_t mode, const float* w_l, const float* w_r, int6
                    : tc_prep_dgrad(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, st);
 }
 
+static thread_local PrepBatch t_prep_batch;
+
+void prep_batch_begin() { t_prep_batch.n_jobs = 0; t_prep_batch.first_block[0] = 0; }
+
+int32_t prep_batch_add(int32_t mode, const float* w_l, const float* w_r, int64_t F, int64_t O, void* ws, size_t ws_bytes) {
+  if (g_force_simt || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
+  PrepBatch& b = t_prep_batch;
+  if (b.n_jobs >= PREP_MAX_JOBS) return NGNN_E_UNSUPPORTED;
+  PrepParams pp{};
+  const int32_t rc = mode == 0 ? tc_prep_fwd(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, nullptr, &pp)
+                               : tc_prep_dgrad(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, nullptr, &pp);
+  if (rc != NGNN_OK) return rc;
+  b.job[b.n_jobs] = pp;
+  b.first_block[b.n_jobs + 1] = b.first_block[b.n_jobs] + (int32_t)ceil_div((int64_t)pp.rows_out * pp.Kpack, 256);
+  ++b.n_jobs;
+  return NGNN_OK;
+}
+
+int32_t prep_batch_launch(cudaStream_t st) {
+  const PrepBatch& b = t_prep_batch;
+  if (b.n_jobs == 0) return NGNN_OK;
+  k_prep_weights_batch<<<(unsigned)b.first_block[b.n_jobs], 256, 0, st>>>(b);
+  NGNN_LAUNCH_CHECK();
+  return NGNN_OK;
+}
+
 int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l, const float* w_r,
                       const float* bias, int64_t n, int64_t F, int64_t O, int32_t act, float drop_p, uint64_t seed,
                       uint64_t offset, float* out, int64_t ld_out, int32_t* path, void* ws, size_t ws_bytes, cudaStream_t st,

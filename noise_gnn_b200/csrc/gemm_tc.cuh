@@ -256,8 +256,7 @@ struct PrepParams {
   int32_t rows_out;
   float *hi, *lo;
 };
-__global__ void k_prep_weights(PrepParams p) {
-  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__device__ __forceinline__ void prep_weights_element(const PrepParams& p, int64_t idx) {
   const int64_t total = (int64_t)p.rows_out * p.Kpack;
   if (idx >= total) return;
   const int32_t ro = (int32_t)(idx / p.Kpack), ko = (int32_t)(idx - (int64_t)ro * p.Kpack);
@@ -273,6 +272,21 @@ __global__ void k_prep_weights(PrepParams p) {
   split_tf32(v, hi, lo);
   p.hi[idx] = hi;
   p.lo[idx] = lo;
+}
+__global__ void k_prep_weights(PrepParams p) { prep_weights_element(p, blockIdx.x * (int64_t)blockDim.x + threadIdx.x); }
+
+// Every pack of a whole network in ONE launch (the fused step prepares the forward and data-gradient packs of all
+// layers before its first kernel): blocks [first_block[j], first_block[j+1]) work on job j.
+constexpr int PREP_MAX_JOBS = 32;
+struct PrepBatch {
+  PrepParams job[PREP_MAX_JOBS];
+  int32_t first_block[PREP_MAX_JOBS + 1];
+  int32_t n_jobs;
+};
+__global__ void k_prep_weights_batch(const __grid_constant__ PrepBatch b) {
+  int j = 0;
+  while (j + 1 < b.n_jobs && (int32_t)blockIdx.x >= b.first_block[j + 1]) ++j;
+  prep_weights_element(b.job[j], (int64_t)(blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x);
 }
 
 // ----------------------------------------------------------------------------- main kernel
@@ -675,7 +689,7 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
 // Packed hi / lo weight planes of the forward projection ([W_l | W_r], K-major) into ws.  `use_l` / `use_r`: which operand
 // pairs the GEMM will contract (a missing one is zero-filled).
 static inline int32_t tc_prep_fwd(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
-                                  size_t ws_bytes, cudaStream_t st) {
+                                  size_t ws_bytes, cudaStream_t st, PrepParams* collect = nullptr) {
   if (F % 4 != 0 || F < 4 || O < 1) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_fwd_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
   const int32_t Fpad = round_up_i(F, TC_BK), Kpack = 2 * Fpad;
@@ -685,6 +699,7 @@ static inline int32_t tc_prep_fwd(const float* w_l, const float* w_r, bool use_l
   pp.w[0] = use_l ? w_l : nullptr; pp.w[1] = use_r ? w_r : nullptr;
   pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 0; pp.seg_stride = Fpad; pp.Kpack = Kpack; pp.rows_out = (int32_t)O;
   pp.hi = hi; pp.lo = lo;
+  if (collect) { *collect = pp; return NGNN_OK; }
   k_prep_weights<<<(unsigned)ceil_div((int64_t)O * Kpack, 256), 256, 0, st>>>(pp);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;
@@ -742,7 +757,7 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
 // dmean_scaled = rowscale * (dy W_l), dx_root = dy W_r, both in one launch (two N segments).
 // Packed hi / lo planes of [W_l^T ; W_r^T] (rows = F per segment, K = O) for the data gradient.
 static inline int32_t tc_prep_dgrad(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
-                                    size_t ws_bytes, cudaStream_t st) {
+                                    size_t ws_bytes, cudaStream_t st, PrepParams* collect = nullptr) {
   if (F < 1 || O < 1) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_dgrad_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
   const int32_t Kpack = round_up_i(O, TC_BK), Rpad = round_up_i(F, 16);
@@ -753,6 +768,7 @@ static inline int32_t tc_prep_dgrad(const float* w_l, const float* w_r, bool use
   pp.w[0] = use_l ? w_l : nullptr; pp.w[1] = use_r ? w_r : nullptr;
   pp.R = (int32_t)O; pp.C = (int32_t)F; pp.transpose = 1; pp.seg_stride = Rpad; pp.Kpack = Kpack; pp.rows_out = rows;
   pp.hi = hi; pp.lo = lo;
+  if (collect) { *collect = pp; return NGNN_OK; }
   k_prep_weights<<<(unsigned)ceil_div((int64_t)rows * Kpack, 256), 256, 0, st>>>(pp);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;

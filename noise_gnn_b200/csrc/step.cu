@@ -179,31 +179,25 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
   const float p_drop = (train && model->training) ? model->dropout : 0.f;
   int32_t rc;
 
-  // ---------------- split weight planes of every layer, once per step, off the critical path ----------------
+  // ---------------- split weight planes of every layer: ONE launch, before the step's first kernel ----------------
   const bool use_aux = g_use_aux && L > 1;
   if (use_aux) { rc = ensure_aux(); if (rc != NGNN_OK) return rc; }
   bool prep_fwd_ok[16], prep_dg_ok[16];
-  {
-    cudaStream_t ps = as_stream(stream);
-    if (use_aux) {             // under the layer-1 aggregation (which does not read the weights)
-      NGNN_CUDA(cudaEventRecord(g_fork, as_stream(stream)));
-      NGNN_CUDA(cudaStreamWaitEvent(g_aux, g_fork, 0));
-      ps = g_aux;
-    }
-    for (int i = 0; i < L; ++i) {
-      const LayerPlan& lp = pl.layer[i];
-      rc = prep_weights_impl(0, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_fwd, lp.prep_fwd_bytes, ps);
+  prep_batch_begin();
+  for (int i = 0; i < L; ++i) {
+    const LayerPlan& lp = pl.layer[i];
+    rc = prep_batch_add(0, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_fwd, lp.prep_fwd_bytes);
+    if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
+    prep_fwd_ok[i] = rc == NGNN_OK;
+    prep_dg_ok[i] = false;
+    if (train && i > 0) {
+      rc = prep_batch_add(1, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_dg, lp.prep_dg_bytes);
       if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
-      prep_fwd_ok[i] = rc == NGNN_OK;
-      prep_dg_ok[i] = false;
-      if (train && i > 0) {
-        rc = prep_weights_impl(1, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_dg, lp.prep_dg_bytes, ps);
-        if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
-        prep_dg_ok[i] = rc == NGNN_OK;
-      }
+      prep_dg_ok[i] = rc == NGNN_OK;
     }
-    if (use_aux) NGNN_CUDA(cudaEventRecord(g_prep, g_aux));
   }
+  rc = prep_batch_launch(as_stream(stream));
+  if (rc != NGNN_OK) return rc;
 
   // ---------------- forward ----------------
   for (int i = 0; i < L; ++i) {
@@ -225,7 +219,6 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
     }
     if (rc != NGNN_OK) return rc;
     const bool last = i == L - 1;
-    if (i == 0 && use_aux) NGNN_CUDA(cudaStreamWaitEvent(as_stream(stream), g_prep, 0));   // join: weight planes ready
     rc = gemm_fwd_impl(F32(lp.mean), lp.F, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
                        lp.n_dst, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
                        drop_offset + (uint64_t)i, F32(lp.out), lp.ldo, nullptr, base + lp.prep_fwd, lp.prep_fwd_bytes,

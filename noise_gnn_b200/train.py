@@ -100,6 +100,25 @@ class Trainer:
         s = self.stats.tolist()
         return s[0], int(s[1])
 
+    def read_stats_async(self):
+        """Starts the device->host copy of (loss sum, correct count) as of the work enqueued so far and returns a
+        handle for `resolve_stats`; lets a training loop log every step without draining the GPU each time."""
+        ring = self.__dict__.setdefault("_stats_ring", [torch.empty(2, dtype=torch.float32, pin_memory=True) for _ in range(8)])
+        i = self.__dict__.get("_stats_i", 0)
+        self._stats_i = i + 1
+        slot = ring[i % len(ring)]
+        slot.copy_(self.stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return slot, ev
+
+    @staticmethod
+    def resolve_stats(handle):
+        slot, ev = handle
+        ev.synchronize()
+        s = slot.tolist()
+        return s[0], int(s[1])
+
     # ------------------------------------------------------------------ fused step
     def _model_struct(self, training: bool):
         m = self.model
