@@ -23,9 +23,13 @@ static int32_t wgrad_splits(int64_t n, int64_t F, int64_t O) {
   if (s > 1024) s = 1024;
   return (int32_t)s;
 }
-static int32_t colsum_slices(int64_t n) {
-  int64_t s = ceil_div(n, 256);
-  if (s > 296) s = 296;            // ~2 CTAs per SM per 32-column strip
+static int32_t colsum_slices(int64_t n, int64_t O) {
+  // ~2 CTAs per SM over all 32-column strips together; the fixed-order reduce over the slices is one dependent chain
+  // per output column, so fewer slices is also a shorter tail (296 slices cost 24 us in that reduce)
+  const int64_t strips = ceil_div(O, 32);
+  int64_t s = ceil_div(2 * kNumSMs, strips);
+  const int64_t max_s = ceil_div(n, 64);
+  if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   return (int32_t)s;
 }
@@ -163,7 +167,7 @@ int32_t ngnn_set_gemm_path(int32_t mode) {
 size_t ngnn_sage_gemm_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_fwd_ws_bytes(F, O) : 256; }
 size_t ngnn_sage_dgrad_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_dgrad_ws_bytes(F, O) : 256; }
 
-static size_t colsum_ws_bytes(int64_t n, int64_t O) { return align_up((size_t)colsum_slices(n) * (size_t)O * sizeof(float), 256); }
+static size_t colsum_ws_bytes(int64_t n, int64_t O) { return align_up((size_t)colsum_slices(n, O) * (size_t)O * sizeof(float), 256); }
 
 size_t ngnn_sage_wgrad_workspace_bytes(int64_t n, int64_t F, int64_t O) {
   if (n <= 0 || F < 0 || O <= 0) return 256;
@@ -226,7 +230,7 @@ int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_
     }
   }
   if (db) {
-    const int32_t Cs = colsum_slices(n);
+    const int32_t Cs = colsum_slices(n, O);
     const int64_t rows = ceil_div(n, Cs);
     dim3 grid((unsigned)ceil_div(O, 32), (unsigned)Cs);
     k_colsum_partial<<<grid, 256, 0, st>>>(dy, ld_dy, n, O, rows, cpart);

@@ -317,7 +317,7 @@ def test_sage_network_untrimmed_and_trimmed_vs_oracle(dev):
 
 # ------------------------------------------------------------------ sampler: bit-exact vs the C oracle + validity
 @pytest.mark.parametrize("fan,replace", [([15, 10, 5], False), ([10, 5], False), ([25], False), ([3, 3, 3, 3], False),
-                                         ([4, 4], True)])
+                                         ([4, 4], True), ([32, 2], False), ([40], False), ([35, 3], True)])
 def test_sampler_bit_exact_vs_oracle(dev, fan, replace):
     from noise_gnn_b200 import NeighborLoader
     from noise_gnn_b200.synthetic import make_dataset
