@@ -101,4 +101,6 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   return v;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 }  // namespace ngnn

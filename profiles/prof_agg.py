@@ -85,3 +85,29 @@ for v in (104, 106, 113, 114, 204, 206, 213, 214):
     ok = torch.equal(m, ref_m) and torch.equal(r, ref_r)
     run(f"smem-staged v={v} bitwise_equal={ok}")
 _lib.call("ngnn_set_tuning", 5, 0)
+
+# ---- K-AGG-T on the layer-2 backward shape of the same blocks: dY_1 = gate(h_1) * (A^T dmean_2 + droot_2)
+F2 = sh.hidden
+ms, by = [], []
+for b in batches:
+    blk = b.block
+    ext = SAGE.layer_extents(blk, sh.layers)
+    n_dst2, e2, n_src2 = ext[1]
+    colptr_t, row_t = blk.transpose(e2, n_src2)
+    dmean = torch.randn((n_dst2, F2), device=dev)
+    droot = torch.randn((n_dst2, F2), device=dev)
+    h1 = torch.randn((n_src2, F2), device=dev)
+    dx = torch.empty((n_src2, F2), device=dev)
+    flush.sum()
+    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ops.agg_bwd(colptr_t, row_t, dmean, n_src2, dx_root=droot, n_root=n_dst2, act_ref=h1, act_scale=2.0, out=dx)
+    z.record()
+    z.synchronize()
+    ms.append(a.elapsed_time(z))
+    by.append(4 * F2 * (2 * n_dst2 + 2 * n_src2) + 4 * e2 + 4 * (n_src2 + 1))
+ms.sort()
+med = ms[len(ms) // 2]
+gbs = (sum(by) / len(by)) / (med * 1e-3) / 1e9
+print(f"K-AGG-T layer-2 backward (n_src {n_src2}, e {e2}, F {F2}): median {med * 1e3:7.1f} us  {gbs:7.1f} GB/s  {gbs / peak:5.3f} of measured peak "
+      f"(bytes {by[-1] / 1e6:.1f} MB: dmean + droot + gate read, dX written)")
