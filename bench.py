@@ -287,7 +287,9 @@ def run_ours(args):
 
     # ---- per-kernel-class breakdown (untimed extra pass through the autograd variant: one FFI call per kernel class) ----
     breakdown = None
-    if not args.no_breakdown and rank == 0:
+    # (single process only: the autograd variant all-reduces in its optimizer step, so running it on rank 0 alone
+    #  would leave the other ranks' collectives unmatched)
+    if not args.no_breakdown and rank == 0 and world == 1:
         loader.epoch = 0
         it = iter(loader)
         for _ in range(W):

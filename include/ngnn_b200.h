@@ -87,6 +87,14 @@ int32_t ngnn_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const float
                           const int32_t* root_idx, float* root, int64_t ld_root,
                           ngnn_stream_t stream);
 
+/* ---- GCNConv(normalize=False) aggregation (reference src/models/layers/convolution.py:19-23 -> PyG GCNConv: sum over
+ * in-neighbours of the already projected rows, then + bias; no self loops, duplicates counted) ----
+ *   out[i,:] = sum_{p in [rowptr[i],rowptr[i+1])} z[col[p],:] + bias      (bias may be NULL)
+ * Same kernel family as K-AGG without the 1/deg scale.  The backward is ngnn_sage_agg_bwd on the transposed block. */
+int32_t ngnn_gcn_agg_fwd(const int32_t* rowptr, const int32_t* col, const float* z, int64_t ld_z,
+                         int64_t n_dst, int64_t O, const float* bias, float* out, int64_t ld_out,
+                         ngnn_stream_t stream);
+
 /* Development knob for kernel sweeps (profiles/prof_agg.py): key 0 = neighbour rows in flight per lane for
  * F <= 128 (2/4/8, 0 = default), key 1 = CTA size of the aggregation kernels (128/256/512).            */
 int32_t ngnn_set_tuning(int32_t key, int32_t value);
@@ -248,6 +256,34 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
                        const int64_t* target_global, const int64_t* label_global,
                        uint64_t drop_seed, uint64_t drop_offset, float* stats /*[2]*/,
                        float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* The step in two calls, for losses that couple several networks (co-teaching, reference src/pipeline.py:95-142: two
+ * forwards, one joint loss, two backwards).  ngnn_sage_forward = the training-mode forward of ngnn_sage_step (dropout
+ * iff model->training), seed-row logits to logits_out, activations kept in ws; ngnn_sage_backward = its backward from
+ * a caller-supplied top-layer gradient dlogits [bs, out_dim], gradients WRITTEN to grads.  Same ws, block, params and
+ * model for the pair; nothing else may use that ws in between.                                                     */
+int32_t ngnn_sage_forward(const ngnn_sage_model_t* model, const float* params, const ngnn_block_t* block,
+                          const int64_t* max_hop_nodes, const int64_t* max_hop_edges,
+                          const float* table, int64_t ld_table, uint64_t drop_seed, uint64_t drop_offset,
+                          float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+int32_t ngnn_sage_backward(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                           const int64_t* max_hop_nodes, const int64_t* max_hop_edges,
+                           const float* table, int64_t ld_table, const float* dlogits, int64_t ld_dlogits,
+                           void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* ---- co-teaching loss (reference src/utils/losses.py:10-49, CTLoss.forward) without its two host argsorts ----
+ * Per-sample CE of two networks on the same seed rows; network 1 is trained on the num_remember rows with the smallest
+ * loss under network 2 and vice versa (ties broken by row index = a stable argsort).
+ *   target / y_true / clean_mask: label arrays indexed by row_ids[i] when row_ids != NULL (global node ids), else by i;
+ *       clean_mask (uint8, optional) = the reference's noise_or_not, for the pure ratios.
+ *   stats[0..5] += loss_1, loss_2 (means over the selected rows), #correct_1, #correct_2, pure_ratio_1, pure_ratio_2
+ *   dlogits1/2 (optional): gradient of loss_1 / loss_2 w.r.t. logits1 / logits2;   order1/2 (optional, [bs]): row
+ *   indices in ascending loss order (order[:num_remember] = the reference's ind_update, the rest = ind_noisy).
+ *   scratch: 12*bs floats.  num_remember = int((1 - forget_rate) * bs), computed by the caller like the reference. */
+int32_t ngnn_ct_loss(const float* logits1, int64_t ld1, const float* logits2, int64_t ld2, const int64_t* target,
+                     const int64_t* y_true, const int32_t* row_ids, const uint8_t* clean_mask, int64_t bs, int64_t C,
+                     int64_t num_remember, float* stats /*[6]*/, float* dlogits1, int64_t ldd1, float* dlogits2,
+                     int64_t ldd2, int32_t* order1, int32_t* order2, float* scratch, ngnn_stream_t stream);
 
 /* 1 (default): inside ngnn_sage_step the weight gradients of layers >= 2 run on an internal auxiliary stream, forked
  * from / joined back into the caller's stream with events (they are off the backward's critical path); 0: strictly

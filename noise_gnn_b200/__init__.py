@@ -7,6 +7,8 @@ underscore.)  Public surface, mirroring the two third-party entry points the ref
 * ``NeighborLoader``  drop-in for ``torch_geometric.loader.NeighborLoader``  (reference src/pipeline.py:6,75-92,152)
 * ``Data``            minimal ``torch_geometric.data.Data`` bag
 * ``SAGE``            the reference's network module (src/models/layers/sage.py:6-78) with a trimmed fused mode
+* ``GCNConv`` / ``SimpleGCN``  the reference's ``module: 'gcn'`` path (src/models/layers/convolution.py:7-53,
+                      ``GCNConv(normalize=False)``): same kernels, sum instead of mean, linear before aggregation
 * ``ops``             tensor-level wrappers over the C ABI in include/ngnn_b200.h (libngnn_b200.so)
 
 Everything computes in hand-written sm_100a CUDA behind a C ABI; there is no CPU or library fallback —
@@ -22,19 +24,25 @@ def build(force: bool = False, verbose: bool = False):
 
 def __getattr__(name):
     # torch-dependent modules are imported lazily so `import noise_gnn_b200` stays cheap
-    if name in ("SAGEConv",):
-        from .conv import SAGEConv
-        return SAGEConv
+    if name in ("SAGEConv", "GCNConv"):
+        from . import conv
+        return getattr(conv, name)
+    if name == "SimpleGCN":
+        from .gcn import SimpleGCN
+        return SimpleGCN
     if name in ("NeighborLoader", "Data", "Batch"):
         from . import loader
         return getattr(loader, name)
     if name == "SAGE":
         from .sage import SAGE
         return SAGE
-    if name in ("ops", "conv", "loader", "sage", "synthetic", "train", "dp"):
+    if name == "CTLoss":
+        from .losses import CTLoss
+        return CTLoss
+    if name in ("ops", "conv", "loader", "sage", "gcn", "losses", "synthetic", "train", "dp"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)
 
 
-__all__ = ["SAGEConv", "NeighborLoader", "Data", "Batch", "SAGE", "build"]
+__all__ = ["SAGEConv", "GCNConv", "NeighborLoader", "Data", "Batch", "SAGE", "SimpleGCN", "CTLoss", "build"]

@@ -26,6 +26,7 @@ SIGNATURES = {
     "ngnn_gather_rows": (c_int32, [_P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P]),
     "ngnn_sage_agg_fwd": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, c_int64, _P]),
     "ngnn_set_tuning": (c_int32, [c_int32, c_int32]),
+    "ngnn_gcn_agg_fwd": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
     "ngnn_sage_agg_bwd": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64,
                                     c_float, _P, c_int64, _P]),
     "ngnn_sage_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
@@ -46,6 +47,10 @@ SIGNATURES = {
     "ngnn_sage_step_workspace_bytes": (c_size_t, [_P, c_int32, _P, _P]),
     "ngnn_sage_step": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, c_uint64, c_uint64, _P, _P, c_int64, _P,
                                  c_size_t, _P]),
+    "ngnn_sage_forward": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_uint64, c_uint64, _P, c_int64, _P, c_size_t, _P]),
+    "ngnn_sage_backward": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_size_t, _P]),
+    "ngnn_ct_loss": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P,
+                               c_int64, _P, _P, _P, _P]),
     "ngnn_set_step_overlap": (c_int32, [c_int32]),
     "ngnn_probe_enable": (c_int32, [c_int32]),
     "ngnn_probe_read": (c_int32, [_P, c_int32, _P]),

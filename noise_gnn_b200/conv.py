@@ -111,3 +111,43 @@ class SAGEConv(torch.nn.Module):
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, aggr=mean)"
+
+
+class GCNConv(torch.nn.Module):
+    """Drop-in for ``torch_geometric.nn.GCNConv(in, out, normalize=False)`` — the only way the reference builds it
+    (src/models/layers/convolution.py:19-23): ``out = A_sum (x W^T) + bias`` with sum aggregation over in-neighbours,
+    duplicate edges counted, no self loops, no symmetric normalisation.  Parameter names follow PyG
+    (``lin.weight [O, F]`` glorot-initialised, ``bias [O]`` zeros) so state_dicts interchange."""
+
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False, cached: bool = False,
+                 add_self_loops=None, normalize: bool = True, bias: bool = True, **kwargs):
+        super().__init__()
+        if normalize:
+            raise NotImplementedError("GCNConv(normalize=True) (symmetric normalisation + self loops) is not used by the "
+                                      "reference, which always passes normalize=False")
+        if add_self_loops:
+            raise NotImplementedError("add_self_loops=True is not used by the reference")
+        if improved or cached or kwargs:
+            raise NotImplementedError("unsupported GCNConv arguments for the reference's use (normalize=False only)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Linear(in_channels, out_channels, bias=False)
+        self.bias = torch.nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.lin.weight)     # PyG Linear(weight_initializer='glorot')
+        if self.bias is not None:
+            torch.nn.init.zeros_(self.bias)
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_weight=None) -> torch.Tensor:
+        if edge_weight is not None:
+            raise NotImplementedError("edge_weight is not used by the reference")
+        if not x.is_cuda:
+            raise RuntimeError("noise_gnn_b200.GCNConv runs on CUDA tensors only (no CPU fallback)")
+        if x.dim() != 2 or x.size(1) != self.in_channels:
+            raise ValueError(f"x must be [n, {self.in_channels}], got {tuple(x.shape)}")
+        block = _block_cache.get(edge_index, x.size(0))
+        return ops.GCNConvFunction.apply(x.float(), self.lin.weight, self.bias, block)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, normalize=False)"

@@ -30,6 +30,7 @@ struct AggParams {
   const float* act_ref;    // optional gate: out *= (act_ref > 0 ? act_scale : 0)
   int64_t ld_act;
   float act_scale;
+  const float* bias;       // optional per-column bias added after the reduction (GCNConv: out = A_sum z + b)
   const int32_t* root_idx; // optional fused root gather (fwd): root[i] = x[root_idx[i]]
   float* root;
   int64_t ld_root;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
       if (c >= F4) continue;
       float4 r = acc[v];
       r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+      if (p.bias != nullptr) f4_add(r, __ldg(reinterpret_cast<const float4*>(p.bias) + c));
       if (has_add) f4_add(r, addv[v]);
       if (p.act_ref != nullptr) {
         const float4 h = gate[v];
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
       const int c = c0 + lane + v * 32;
       if (c >= F) continue;
       float r = acc[v] * scale;
+      if (p.bias != nullptr) r += __ldg(p.bias + c);
       if (p.add != nullptr && row < p.n_add) r += __ldg(p.add + row * p.ld_add + c);
       if (p.act_ref != nullptr) r = __ldg(p.act_ref + row * p.ld_act + c) > 0.f ? r * p.act_scale : 0.f;
       p.out[row * p.ld_out + c] = r;
@@ -327,9 +330,10 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
   if (p.add) vec = vec && (p.ld_add % 4 == 0) && is_aligned(p.add, 16);
   if (p.act_ref) vec = vec && (p.ld_act % 4 == 0) && is_aligned(p.act_ref, 16);
   if (p.root_idx) vec = vec && (p.ld_root % 4 == 0) && is_aligned(p.root, 16);
+  if (p.bias) vec = vec && is_aligned(p.bias, 16);
   if (vec) {
     const int64_t F4 = p.F / 4;
-    const bool fwd_plain = p.add == nullptr && p.act_ref == nullptr;      // forward aggregation (mean [+ root gather])
+    const bool fwd_plain = p.add == nullptr && p.act_ref == nullptr && p.bias == nullptr;   // forward aggregation (mean [+ root gather])
     if (fwd_plain && g_tune_bulk && F4 <= 32 && p.n_rows < (1ll << 31)) {
       const bool ok = p.root_idx ? launch_bulk<true>(p, st, g_tune_bulk) : launch_bulk<false>(p, st, g_tune_bulk);
       if (ok) { NGNN_LAUNCH_CHECK(); return NGNN_OK; }
@@ -404,6 +408,18 @@ int32_t ngnn_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const float
   p.ptr = rowptr; p.idx = col; p.x = x; p.ld_x = ld_x; p.n_rows = n_dst; p.F = F;
   p.out = mean; p.ld_out = ld_mean; p.mean = 1;
   p.root_idx = root_idx; p.root = root; p.ld_root = ld_root;
+  return run_agg(p, as_stream(stream));
+}
+
+int32_t ngnn_gcn_agg_fwd(const int32_t* rowptr, const int32_t* col, const float* z, int64_t ld_z, int64_t n_dst, int64_t O,
+                         const float* bias, float* out, int64_t ld_out, ngnn_stream_t stream) {
+  NGNN_REQUIRE(n_dst >= 0 && O >= 0, NGNN_E_INVALID, "gcn_agg_fwd: negative size");
+  if (n_dst == 0 || O == 0) return NGNN_OK;
+  NGNN_REQUIRE(rowptr && z && out, NGNN_E_INVALID, "gcn_agg_fwd: null pointer");
+  NGNN_REQUIRE(ld_z >= O && ld_out >= O, NGNN_E_INVALID, "gcn_agg_fwd: leading dimension < O");
+  AggParams p{};
+  p.ptr = rowptr; p.idx = col; p.x = z; p.ld_x = ld_z; p.n_rows = n_dst; p.F = O;
+  p.out = out; p.ld_out = ld_out; p.mean = 0; p.bias = bias;
   return run_agg(p, as_stream(stream));
 }
 

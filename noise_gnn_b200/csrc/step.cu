@@ -156,11 +156,14 @@ size_t ngnn_sage_step_workspace_bytes(const ngnn_sage_model_t* model, int32_t nu
   return pl.total;
 }
 
-int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
-                       const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
-                       const int64_t* target_global, const int64_t* label_global, uint64_t drop_seed, uint64_t drop_offset,
-                       float* stats, float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
-  NGNN_REQUIRE(model && params && block && table && stats && ws, NGNN_E_INVALID, "sage_step: null pointer");
+// phase 0: forward + loss + backward (ngnn_sage_step); phase 1: training-mode forward only, activations stay in ws
+// (ngnn_sage_forward); phase 2: backward only from a caller-supplied top-layer gradient (ngnn_sage_backward).
+static int32_t sage_step_impl(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                              const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
+                              const int64_t* target_global, const int64_t* label_global, uint64_t drop_seed, uint64_t drop_offset,
+                              float* stats, float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream,
+                              int32_t phase, const float* dlogits_in, int64_t ld_dlogits) {
+  NGNN_REQUIRE(model && params && block && table && ws && (stats || phase != 0), NGNN_E_INVALID, "sage_step: null pointer");
   NGNN_REQUIRE(block->rowptr && block->col && block->col_global && block->n_id && block->hop_nodes && block->hop_edges,
                NGNN_E_INVALID, "sage_step: incomplete block");
   NGNN_REQUIRE(model->dropout >= 0.f && model->dropout < 1.f, NGNN_E_INVALID, "sage_step: dropout outside [0,1)");
@@ -169,8 +172,10 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
                NGNN_E_INVALID, "sage_step: bad model / block extents (block larger than the declared capacity?)");
   NGNN_REQUIRE(ws_bytes >= pl.total, NGNN_E_WORKSPACE, "sage_step: workspace too small (%zu < %zu)", ws_bytes, pl.total);
   NGNN_REQUIRE(ld_table >= model->in_dim, NGNN_E_INVALID, "sage_step: ld_table < in_dim");
-  const bool train = grads != nullptr;
-  NGNN_REQUIRE(!train || target_global != nullptr, NGNN_E_INVALID, "sage_step: training needs targets");
+  const bool train = grads != nullptr || phase != 0;
+  NGNN_REQUIRE(!train || phase != 0 || target_global != nullptr, NGNN_E_INVALID, "sage_step: training needs targets");
+  NGNN_REQUIRE(phase != 2 || (grads != nullptr && dlogits_in != nullptr && ld_dlogits >= model->out_dim), NGNN_E_INVALID,
+               "sage_backward: needs the gradient bucket and dlogits");
   char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(ws), 256));
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   auto I32 = [&](size_t off) { return reinterpret_cast<int32_t*>(base + off); };
@@ -196,11 +201,13 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
       prep_dg_ok[i] = rc == NGNN_OK;
     }
   }
-  rc = prep_batch_launch(as_stream(stream));
-  if (rc != NGNN_OK) return rc;
+  if (phase != 2) {          // phase 2: the planes of the matching forward call are still valid (weights unchanged)
+    rc = prep_batch_launch(as_stream(stream));
+    if (rc != NGNN_OK) return rc;
+  }
 
   // ---------------- forward ----------------
-  for (int i = 0; i < L; ++i) {
+  for (int i = 0; i < L && phase != 2; ++i) {
     const LayerPlan& lp = pl.layer[i];
     const float* root;
     int64_t ld_root;
@@ -226,18 +233,24 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
     if (rc != NGNN_OK) return rc;
   }
   const LayerPlan& top = pl.layer[L - 1];
-  if (logits_out) {
+  if (logits_out && phase != 2) {
     NGNN_REQUIRE(ld_logits >= top.O, NGNN_E_INVALID, "sage_step: ld_logits < out_dim");
     NGNN_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)ld_logits * 4, F32(top.out), (size_t)top.ldo * 4, (size_t)top.O * 4, (size_t)bs,
                                 cudaMemcpyDeviceToDevice, as_stream(stream)));
   }
-  if (target_global == nullptr) return NGNN_OK;   // inference: forward only
+  if (phase == 1) return NGNN_OK;                 // forward of a split step: the caller computes the loss gradient
+  if (phase == 2) {                               // top-layer gradient supplied by the caller (e.g. the co-teaching loss)
+    NGNN_CUDA(cudaMemcpy2DAsync(F32(top.dy), (size_t)top.ldo * 4, dlogits_in, (size_t)ld_dlogits * 4, (size_t)top.O * 4,
+                                (size_t)bs, cudaMemcpyDeviceToDevice, as_stream(stream)));
+  } else {
+    if (target_global == nullptr) return NGNN_OK;   // inference: forward only
 
-  // ---------------- loss on the seed rows (labels gathered by global id) ----------------
-  rc = ngnn_ce_fwd_bwd_gather(F32(top.out), top.ldo, target_global, label_global, block->n_id, bs, top.O, 1.0f, stats,
-                              train ? F32(top.dy) : nullptr, top.ldo, F32(pl.ce_rows), stream);
-  if (rc != NGNN_OK) return rc;
-  if (!train) return NGNN_OK;
+    // ---------------- loss on the seed rows (labels gathered by global id) ----------------
+    rc = ngnn_ce_fwd_bwd_gather(F32(top.out), top.ldo, target_global, label_global, block->n_id, bs, top.O, 1.0f, stats,
+                                train ? F32(top.dy) : nullptr, top.ldo, F32(pl.ce_rows), stream);
+    if (rc != NGNN_OK) return rc;
+    if (!train) return NGNN_OK;
+  }
 
   // ---------------- backward ----------------
   bool aux_used = false;
@@ -295,6 +308,30 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
     NGNN_CUDA(cudaStreamWaitEvent(as_stream(stream), g_join, 0));
   }
   return NGNN_OK;
+}
+
+int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                       const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
+                       const int64_t* target_global, const int64_t* label_global, uint64_t drop_seed, uint64_t drop_offset,
+                       float* stats, float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  return sage_step_impl(model, params, grads, block, max_hop_nodes, max_hop_edges, table, ld_table, target_global, label_global,
+                        drop_seed, drop_offset, stats, logits_out, ld_logits, ws, ws_bytes, stream, 0, nullptr, 0);
+}
+
+int32_t ngnn_sage_forward(const ngnn_sage_model_t* model, const float* params, const ngnn_block_t* block,
+                          const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
+                          uint64_t drop_seed, uint64_t drop_offset, float* logits_out, int64_t ld_logits, void* ws,
+                          size_t ws_bytes, ngnn_stream_t stream) {
+  NGNN_REQUIRE(logits_out != nullptr, NGNN_E_INVALID, "sage_forward: logits_out is null");
+  return sage_step_impl(model, params, nullptr, block, max_hop_nodes, max_hop_edges, table, ld_table, nullptr, nullptr, drop_seed,
+                        drop_offset, nullptr, logits_out, ld_logits, ws, ws_bytes, stream, 1, nullptr, 0);
+}
+
+int32_t ngnn_sage_backward(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                           const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
+                           const float* dlogits, int64_t ld_dlogits, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  return sage_step_impl(model, params, grads, block, max_hop_nodes, max_hop_edges, table, ld_table, nullptr, nullptr, 0, 0,
+                        nullptr, nullptr, 0, ws, ws_bytes, stream, 2, dlogits, ld_dlogits);
 }
 
 int32_t ngnn_set_step_overlap(int32_t on) { g_use_aux = on != 0; return NGNN_OK; }

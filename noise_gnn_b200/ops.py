@@ -189,6 +189,18 @@ def agg_fwd(rowptr, col, x, n_dst: int, root_idx=None, out=None, root_out=None, 
     return (mean, root) if root_idx is not None else mean
 
 
+def gcn_agg_fwd(rowptr, col, z, n_dst: int, bias=None, out=None, tag=None):
+    """out[i] = sum_{p} z[col[p]] + bias  (GCNConv(normalize=False) propagation: sum, duplicates counted, no self loops)."""
+    _check_cuda(rowptr, col, z, bias)
+    z = _rows(z, "z")
+    O = z.size(1)
+    y = out if out is not None else torch.empty((n_dst, O), dtype=_F32, device=z.device)
+    with _timed(tag or "gcn_agg_fwd"):
+        _lib.call("ngnn_gcn_agg_fwd", _ptr(rowptr), _ptr(col), _ptr(z), _ld(z), n_dst, O,
+                  _ptr(bias.contiguous() if bias is not None else None), _ptr(y), _ld(y), _stream())
+    return y
+
+
 def agg_bwd(colptr_t, row_t, dmean_scaled, n_src: int, dx_root=None, n_root: int = 0, act_ref=None,
             act_scale: float = 1.0, out=None, tag=None):
     _check_cuda(colptr_t, row_t, dmean_scaled)
@@ -303,6 +315,35 @@ def ce_fwd_bwd(logits, target, y_true=None, grad_scale: float = 1.0, stats=None,
     return stats, dlogits
 
 
+def ct_loss(logits1, logits2, target, num_remember: int, y_true=None, row_ids=None, clean_mask=None, stats=None,
+            want_grad: bool = True, want_order: bool = False):
+    """Co-teaching loss (reference src/utils/losses.py:10-49) on the device.  Returns (stats[6], dlogits1, dlogits2,
+    order1, order2): stats += [loss_1, loss_2, correct_1, correct_2, pure_ratio_1, pure_ratio_2]."""
+    _check_cuda(logits1, logits2, target)
+    logits1, logits2 = _rows(logits1, "logits1"), _rows(logits2, "logits2")
+    bs, C = logits1.shape
+    dev = logits1.device
+    target = target.contiguous()
+    if target.dtype != torch.int64:
+        target = target.long()
+    if y_true is not None:
+        y_true = y_true.long().contiguous() if y_true.dtype != torch.int64 else y_true.contiguous()
+    if clean_mask is not None:
+        clean_mask = clean_mask.to(torch.uint8).contiguous()
+    if stats is None:
+        stats = torch.zeros(6, dtype=_F32, device=dev)
+    d1 = torch.empty((bs, C), dtype=_F32, device=dev) if want_grad else None
+    d2 = torch.empty((bs, C), dtype=_F32, device=dev) if want_grad else None
+    o1 = torch.empty(bs, dtype=_I32, device=dev) if want_order else None
+    o2 = torch.empty(bs, dtype=_I32, device=dev) if want_order else None
+    scratch = torch.empty(12 * max(bs, 1), dtype=_F32, device=dev)
+    with _timed("ct_loss"):
+        _lib.call("ngnn_ct_loss", _ptr(logits1), _ld(logits1), _ptr(logits2), _ld(logits2), _ptr(target), _ptr(y_true),
+                  _ptr(row_ids), _ptr(clean_mask), bs, C, int(num_remember), _ptr(stats), _ptr(d1), _ld(d1) if d1 is not None else 0,
+                  _ptr(d2), _ld(d2) if d2 is not None else 0, _ptr(o1), _ptr(o2), _ptr(scratch), _stream())
+    return stats, d1, d2, o1, o2
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
               grad_scale=1.0, advance_step=True):
     _check_cuda(param, grad, exp_avg, exp_avg_sq, step_dev)
@@ -346,3 +387,40 @@ class SAGEConvFunction(torch.autograd.Function):
             colptr_t, row_t = block.transpose(e_limit, x.size(0))
             dx = agg_bwd(colptr_t, row_t, dmean, x.size(0), dx_root=droot, n_root=n_dst)
         return dx, dw_l, db, dw_r, None, None, None
+
+
+# ----------------------------------------------------------------------------- GCNConv autograd
+class GCNConvFunction(torch.autograd.Function):
+    """out = A_sum (x W^T) + b on a CSR block (PyG GCNConv(normalize=False): linear first, then sum over in-neighbours).
+
+    forward:  z = x W^T  (K-GEMM, single operand)  ->  out = segment-sum(z) + b   (K-AGG without the 1/deg scale)
+    backward: db = colsum(dOut);  dZ = A^T dOut (K-AGG-T);  dW = dZ^T x (K-WGRAD);  dX = dZ W (K-DGRAD)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, block: Block):
+        x = _rows(x, "x")
+        n = x.size(0)
+        z = gemm_fwd(None, x, None, weight, None, n)
+        out = gcn_agg_fwd(block.rowptr, block.col, z, n, bias=bias)
+        ctx.save_for_backward(x, weight)
+        ctx.block, ctx.has_bias = block, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight = ctx.saved_tensors
+        block = ctx.block
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        dout = _rows(dout, "dout")
+        n, F_ = x.size(0), x.size(1)
+        dx = dw = db = None
+        if need_b and ctx.has_bias:
+            _, _, db = wgrad(dout, None, None, n, F_, want_l=False, want_r=False, want_b=True)
+        if need_x or need_w:
+            colptr_t, row_t = block.transpose(block.e, n)
+            dz = agg_bwd(colptr_t, row_t, dout, n)
+            if need_w:
+                _, dw, _ = wgrad(dz, None, x, n, F_, want_l=False, want_r=True, want_b=False)
+            if need_x:
+                _, dx = dgrad(dz, None, weight, None, n, want_mean=False, want_root=True)
+        return dx, dw, db, None

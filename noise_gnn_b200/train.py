@@ -186,6 +186,47 @@ class Trainer:
             prefetch()
         return logits
 
+    # ------------------------------------------------------------------ split step (losses that couple several networks)
+    def _block_desc(self, batch):
+        blk = batch.block
+        H = len(blk.hop_nodes) - 1
+        hop_n = (ctypes.c_int32 * (H + 1))(*blk.hop_nodes)
+        hop_e = (ctypes.c_int32 * (H + 1))(*blk.hop_edges)
+        bd = _lib.BlockDesc(blk.rowptr.data_ptr(), blk.col.data_ptr(), blk.col_global.data_ptr(), blk.n_id.data_ptr(), H,
+                            hop_n, hop_e)
+        need = min(self._cfg["num_layers"] - 1, H)
+        batch._loader.transpose_hops = max(batch._loader.transpose_hops, need)
+        for b in range(1, min(need, 7) + 1):
+            pre = blk._t.get((blk.hop_edges[b], blk.hop_nodes[b]))
+            if pre is not None:
+                bd.colptr_t[b], bd.row_t[b] = pre[0].data_ptr(), pre[1].data_ptr()
+        return bd, (hop_n, hop_e)
+
+    def forward_only(self, batch):
+        """Training-mode forward (ngnn_sage_forward): seed-row logits; activations stay in the arena for backward_from."""
+        loader = batch._loader
+        ms = self._model_struct(training=self.model.training)
+        arena = self._ensure_arena(loader, ms)
+        bd, keep = self._block_desc(batch)
+        logits = torch.empty((batch.batch_size, self._cfg["out_dim"]), dtype=torch.float32, device=arena.device)
+        self.steps += 1
+        _lib.call("ngnn_sage_forward", ctypes.byref(ms), ops._ptr(self.buckets.param), ctypes.byref(bd), self._max_nodes,
+                  self._max_edges, ops._ptr(loader.x), loader.x.stride(0), self.model.drop_seed,
+                  self.steps * self._cfg["num_layers"], ops._ptr(logits), logits.stride(0), ops._ptr(arena), arena.numel(),
+                  ops._stream())
+        return logits
+
+    def backward_from(self, batch, dlogits):
+        """Backward of the preceding forward_only on the same batch from d(loss)/d(logits) (ngnn_sage_backward)."""
+        loader = batch._loader
+        ms = self._model_struct(training=self.model.training)
+        arena = self._ensure_arena(loader, ms)
+        bd, keep = self._block_desc(batch)
+        dlogits = ops._rows(dlogits, "dlogits")
+        _lib.call("ngnn_sage_backward", ctypes.byref(ms), ops._ptr(self.buckets.param), ops._ptr(self.buckets.grad),
+                  ctypes.byref(bd), self._max_nodes, self._max_edges, ops._ptr(loader.x), loader.x.stride(0),
+                  ops._ptr(dlogits), ops._ld(dlogits), ops._ptr(arena), arena.numel(), ops._stream())
+
     # ------------------------------------------------------------------ autograd variant (same kernels, ~80 FFI calls)
     def train_step_autograd(self, batch, target_attr: str = "yhn", label_attr: Optional[str] = "y"):
         model, bk = self.model, self.buckets
@@ -199,3 +240,42 @@ class Trainer:
         bk.rebind_grads()
         self.optimizer_step()
         return logits
+
+
+class CoTeachingTrainer:
+    """Loop body of ``PipelineCO.train_ct`` (reference src/pipeline.py:111-133) for two peer SAGE networks on the fused
+    path: two ngnn_sage_forward calls on the same block, ONE ngnn_ct_loss (device-side small-loss selection and exchange,
+    reference src/utils/losses.py:19-49 without its two host argsorts), two ngnn_sage_backward calls, two Adam steps.
+    Nothing in the step synchronises with the host; ``stats`` accumulates
+    [loss_1, loss_2, correct_1, correct_2, pure_ratio_1, pure_ratio_2] sums for the epoch logging."""
+
+    def __init__(self, model1, model2, lr: float = 1e-3, **adam):
+        self.t1, self.t2 = Trainer(model1, lr=lr, **adam), Trainer(model2, lr=lr, **adam)
+        self.stats = torch.zeros(6, dtype=torch.float32, device=self.t1.buckets.param.device)
+
+    def reset_stats(self):
+        self.stats.zero_()
+
+    def read_stats(self):
+        return self.stats.tolist()
+
+    def train_step(self, batch, forget_rate: float, target_attr: str = "yhn", label_attr: Optional[str] = "y",
+                   clean_attr: Optional[str] = None):
+        loader, blk = batch._loader, batch.block
+        bs = batch.batch_size
+        out1 = self.t1.forward_only(batch)
+        out2 = self.t2.forward_only(batch)
+        num_remember = int((1 - forget_rate) * bs)                       # reference losses.py:28-29
+        tgt = loader.label_array(target_attr)
+        lab = loader.label_array(label_attr) if label_attr else None
+        clean = loader.node_attrs[clean_attr].view(-1) if clean_attr else None
+        _, d1, d2, _, _ = ops.ct_loss(out1, out2, tgt, num_remember, y_true=lab, row_ids=blk.n_id, clean_mask=clean,
+                                      stats=self.stats)
+        self.t1.backward_from(batch, d1)
+        self.t1.optimizer_step()
+        self.t2.backward_from(batch, d2)
+        self.t2.optimizer_step()
+        prefetch = getattr(batch, "_prefetch", None)
+        if prefetch is not None:
+            prefetch()
+        return out1, out2

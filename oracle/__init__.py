@@ -15,6 +15,9 @@ restates the published algorithms, anchored on the reference's call sites:
                        (index_select -> scatter_add_ -> count -> clamp(min=1) -> divide -> linear x2 -> add),
                        network structure verbatim from reference src/models/layers/sage.py:6-40,
                        train step from reference src/pipeline.py:144-173.
+                       Also ``GCNConvRef`` / ``SimpleGCNRef``: PyG ``GCNConv(normalize=False)`` as built at reference
+                       src/models/layers/convolution.py:19-23 (linear, then sum over in-neighbours, + bias).
+* ``ct_oracle``        ``CTLoss.forward`` of reference src/utils/losses.py:19-49 restated line by line (stable argsort).
 * ``structure``        COO -> CSR by destination (stable), CSR transpose — numpy.
 * ``sampler``          ctypes binding of ``sampler_oracle.c`` (sequential fan-out sampler with the same
                        Philox4x32-10 stream as the CUDA sampler) plus a pure-Python twin for tiny cases.

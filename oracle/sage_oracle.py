@@ -54,6 +54,46 @@ class SAGEConvRef(torch.nn.Module):
         return out
 
 
+class GCNConvRef(torch.nn.Module):
+    """``torch_geometric.nn.GCNConv(in, out, normalize=False)`` as the reference builds it
+    (src/models/layers/convolution.py:19-23): ``x = lin(x)`` (no bias), messages ``x.index_select(0, src)`` summed by
+    ``scatter_add_`` over dst (aggr='add'; no self loops and no symmetric norm because normalize=False), then ``+ bias``.
+    Parameter names as in PyG: ``lin.weight`` (glorot), ``bias`` (zeros)."""
+
+    def __init__(self, in_channels: int, out_channels: int, dtype=torch.float32):
+        super().__init__()
+        self.lin = torch.nn.Linear(in_channels, out_channels, bias=False, dtype=dtype)
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels, dtype=dtype))
+        torch.nn.init.xavier_uniform_(self.lin.weight)
+
+    def forward(self, x, edge_index):
+        z = self.lin(x)
+        src, dst = edge_index[0], edge_index[1]
+        msg = z.index_select(0, src)
+        out = z.new_zeros(z.shape).scatter_add_(0, dst.view(-1, 1).expand_as(msg), msg)
+        return out + self.bias
+
+
+class SimpleGCNRef(torch.nn.Module):
+    """Structure of reference src/models/layers/convolution.py:7-35."""
+
+    def __init__(self, in_size, hidden_size, out_size, num_layers, dropout=0.5, dtype=torch.float32):
+        super().__init__()
+        self.num_layers, self.dropout = num_layers, dropout
+        self.convs = torch.nn.ModuleList([GCNConvRef(in_size, hidden_size, dtype=dtype)])
+        for _ in range(num_layers - 2):
+            self.convs.append(GCNConvRef(hidden_size, hidden_size, dtype=dtype))
+        self.convs.append(GCNConvRef(hidden_size, out_size, dtype=dtype))
+
+    def forward(self, x, edge_index):
+        for i, conv in enumerate(self.convs):
+            x = conv(x, edge_index)
+            if i != self.num_layers - 1:
+                x = x.relu()
+                x = F.dropout(x, p=self.dropout, training=self.training)
+        return x
+
+
 class SAGERef(torch.nn.Module):
     """Structure of reference src/models/layers/sage.py:6-40 (use_bn is dead in the reference: no caller sets it)."""
 

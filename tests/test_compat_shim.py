@@ -30,8 +30,10 @@ def test_shim_exposes_only_the_hot_path(shim_on_path):
     from torch_geometric.nn import GCNConv, SAGEConv
     import noise_gnn_b200
     assert SAGEConv is noise_gnn_b200.SAGEConv and NeighborLoader is noise_gnn_b200.NeighborLoader and Data is noise_gnn_b200.Data
+    assert GCNConv is noise_gnn_b200.GCNConv
     with pytest.raises(NotImplementedError):
-        GCNConv(4, 4)
+        GCNConv(4, 4)                               # normalize=True (PyG's default) is not what the reference builds
+    assert sorted(GCNConv(4, 4, normalize=False).state_dict()) == ["bias", "lin.weight"]
     from torch_geometric.datasets import Planetoid
     with pytest.raises(NotImplementedError):
         Planetoid(root="x", name="pubmed")
@@ -48,4 +50,23 @@ def test_reference_sage_module_builds_on_the_drop_in(shim_on_path):
     ours = noise_gnn_b200.SAGE(100, 256, 47, 3, dropout=0.5)
     assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
     ours.load_state_dict(net.state_dict())      # state_dicts interchange (PyG parameter names)
+    net.reset_parameters()
+
+
+REF_GCN = "/root/reference/src/models/layers/convolution.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GCN), reason="reference tree only exists in the builder container")
+def test_reference_simplegcn_module_builds_on_the_drop_in(shim_on_path):
+    """reference src/models/layers/convolution.py (unmodified) constructs on the drop-in GCNConv, with the same
+    state_dict layout as noise_gnn_b200.SimpleGCN."""
+    spec = importlib.util.spec_from_file_location("ref_gcn", REF_GCN)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import noise_gnn_b200
+    net = mod.SimpleGCN(128, 256, 40, 3, dropout=0.5)
+    assert all(isinstance(c, noise_gnn_b200.GCNConv) for c in net.convs)
+    ours = noise_gnn_b200.SimpleGCN(128, 256, 40, 3, dropout=0.5)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    ours.load_state_dict(net.state_dict())
     net.reset_parameters()

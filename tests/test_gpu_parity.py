@@ -286,6 +286,61 @@ def test_sageconv_forward_backward_vs_oracle(dev, n, e, F, O, sort):
     assert rel_err(x.grad, x64.grad) < RTOL
 
 
+# ------------------------------------------------------------------ GCN path (reference convolution.py:7-53, module 'gcn')
+@pytest.mark.parametrize("n,e,F,O,sort", [(500, 4000, 100, 256, True), (500, 4000, 256, 47, False),
+                                          (300, 2500, 1433, 7, False), (800, 0, 64, 16, True),
+                                          (1, 3, 8, 4, True), (400, 3000, 767, 10, True), (2000, 30000, 128, 40, False)])
+def test_gcnconv_forward_backward_vs_oracle(dev, n, e, F, O, sort):
+    """GCNConv(normalize=False): out = A_sum (x W^T) + b — unsorted COO, duplicate edges, zero in-degree rows,
+    widths the tcgen05 path takes (F % 4 == 0) and the ones it cannot (1433, 767)."""
+    from noise_gnn_b200 import GCNConv
+    torch.manual_seed(n + F)
+    ei = random_coo(n, e, seed=e + 1, sort=sort)
+    if e > 20:
+        ei[:, 10] = ei[:, 11]                      # a duplicated edge
+    ref = sage_oracle.GCNConvRef(F, O, dtype=torch.float64)
+    with torch.no_grad():
+        ref.bias.normal_()                         # PyG initialises the bias to zero; make it visible to the test
+    conv = GCNConv(F, O, normalize=False).to(dev)
+    assert sorted(conv.state_dict()) == sorted(ref.state_dict()) == ["bias", "lin.weight"]
+    conv.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    x64 = torch.randn(n, F, dtype=torch.float64, requires_grad=True)
+    x = x64.detach().float().to(dev).requires_grad_(True)
+    gout = torch.randn(n, O, dtype=torch.float64)
+    o_ref = ref(x64, ei)
+    (o_ref * gout).sum().backward()
+    o = conv(x, ei.to(dev))
+    (o * gout.float().to(dev)).sum().backward()
+    assert rel_err(o, o_ref) < RTOL
+    assert rel_err(conv.lin.weight.grad, ref.lin.weight.grad) < RTOL
+    assert rel_err(conv.bias.grad, ref.bias.grad) < RTOL
+    assert rel_err(x.grad, x64.grad) < RTOL
+
+
+def test_simplegcn_network_on_a_sampled_block_vs_oracle(dev):
+    """The reference's SimpleGCN (3 x GCNConv, relu between) on an identical sampled block: seed-row logits, loss and
+    every parameter gradient against the fp64 oracle network."""
+    from noise_gnn_b200 import NeighborLoader, SimpleGCN
+    from noise_gnn_b200.synthetic import make_dataset
+    data, sh, train_idx = make_dataset("arxiv", scale=0.02, device="cpu")
+    loader = NeighborLoader(data, input_nodes=train_idx, num_neighbors=[10, 5], batch_size=64, shuffle=True)
+    batch = next(iter(loader))
+    torch.manual_seed(1232)
+    ref = sage_oracle.SimpleGCNRef(sh.features, 64, sh.classes, 3, dropout=0.0, dtype=torch.float64)
+    net = SimpleGCN(sh.features, 64, sh.classes, 3, dropout=0.0).to(dev)
+    net.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    bs = batch.batch_size
+    tgt = batch.yhn[:bs].view(-1).cpu()
+    loss_ref = torch.nn.functional.cross_entropy(ref(batch.x.cpu().double(), batch.edge_index.cpu())[:bs], tgt)
+    loss_ref.backward()
+    out = net(batch.x, batch.edge_index)[:bs]
+    loss = torch.nn.functional.cross_entropy(out, tgt.to(dev))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) < 1e-5 * max(1.0, abs(float(loss_ref.detach())))
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad, q.grad) < 2e-5, k
+
+
 def test_sage_network_untrimmed_and_trimmed_vs_oracle(dev):
     """Reference-exact mode and the trimmed fused mode both reproduce the oracle network's seed rows and
     parameter gradients on an identical sampled block (dropout off: RNG streams are not comparable)."""

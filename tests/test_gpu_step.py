@@ -156,3 +156,77 @@ def test_fused_step_on_every_baseline_config_shape(dev, name, scale, hidden):
     assert rel_err(logits, out_ref) < 1e-5
     for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
         assert rel_err(p.grad, q.grad) < 2e-5, (name, k)
+
+
+# ------------------------------------------------------------------ co-teaching (reference pipeline.py:95-142, losses.py:10-49)
+@pytest.mark.parametrize("bs,C,forget", [(300, 7, 0.2), (512, 47, 0.5), (64, 3, 0.0), (1000, 40, 0.35)])
+def test_ct_loss_matches_oracle(dev, bs, C, forget):
+    """The drop-in CTLoss (device-side ranking) against the line-by-line restatement of the reference's CTLoss:
+    both exchanged losses, both pure ratios, the four index lists (bit-exact), and the gradients w.r.t. both logits."""
+    from noise_gnn_b200 import CTLoss
+    from oracle import ct_oracle
+    g = torch.Generator().manual_seed(bs + C)
+    y1 = torch.randn(bs, C, generator=g, dtype=torch.float64)
+    y2 = torch.randn(bs, C, generator=g, dtype=torch.float64)
+    # fp32-representable inputs so both sides rank the very same numbers
+    y1, y2 = y1.float().double().requires_grad_(True), y2.float().double().requires_grad_(True)
+    yn = torch.randint(0, C, (bs,), generator=g)
+    N = 5 * bs
+    ind = torch.randperm(N, generator=g)[:bs + 50]                  # batch.n_id: seeds first, more nodes after
+    noise_or_not = torch.rand(N, generator=g) < 0.7
+    want = ct_oracle.ct_loss(y1, y2, yn, forget, ind, noise_or_not)
+    (want[0] * 1.5 + want[1] * 0.5).backward()
+    a1 = y1.detach().float().to(dev).requires_grad_(True)
+    a2 = y2.detach().float().to(dev).requires_grad_(True)
+    got = CTLoss(dev)(a1, a2, yn.to(dev), forget, ind.to(dev), noise_or_not.to(dev))
+    (got[0] * 1.5 + got[1] * 0.5).backward()
+    # fp32 vs fp64 per-sample losses can order near-ties differently; compare the selections as sets when they differ in order
+    for k in (4, 5, 6, 7):
+        assert sorted(got[k].cpu().tolist()) == sorted(want[k].tolist()), k
+    assert rel_err(got[0].detach(), want[0].detach()) < 1e-5 and rel_err(got[1].detach(), want[1].detach()) < 1e-5
+    assert abs(float(got[2]) - float(want[2])) < 1e-6 and abs(float(got[3]) - float(want[3])) < 1e-6
+    assert rel_err(a1.grad, y1.grad) < 1e-5 and rel_err(a2.grad, y2.grad) < 1e-5
+
+
+def test_coteaching_step_matches_oracle(dev):
+    """CoTeachingTrainer.train_step (2 x ngnn_sage_forward, ngnn_ct_loss, 2 x ngnn_sage_backward, 2 x Adam) against two
+    fp64 oracle networks + the oracle CTLoss on the identical sampled block: both exchanged losses and every parameter
+    gradient of both networks."""
+    from noise_gnn_b200 import NeighborLoader, SAGE
+    from noise_gnn_b200.synthetic import make_dataset
+    from noise_gnn_b200.train import CoTeachingTrainer
+    from oracle import ct_oracle
+    data, sh, train_idx = make_dataset("arxiv", scale=0.02, device="cpu", noise_type="sym", noise_rate=0.3)
+    data.clean = (data.yhn.view(-1) == data.y.view(-1))
+    loader = NeighborLoader(data, input_nodes=train_idx, num_neighbors=[10, 5], batch_size=128, shuffle=True, seed=1232)
+    batch = next(iter(loader))
+    bs = batch.batch_size
+    refs, nets = [], []
+    for s in (1, 2):
+        torch.manual_seed(s)
+        ref = sage_oracle.SAGERef(sh.features, 64, sh.classes, 3, dropout=0.0, dtype=torch.float64)
+        net = SAGE(sh.features, 64, sh.classes, 3, dropout=0.0).to(dev)
+        net.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+        net.train()
+        refs.append(ref); nets.append(net)
+    x_cpu, ei_cpu = batch.x.cpu().double(), batch.edge_index.cpu()
+    yhn = batch.yhn[:bs].view(-1).cpu()
+    o1, o2 = refs[0](x_cpu, ei_cpu)[:bs], refs[1](x_cpu, ei_cpu)[:bs]
+    forget = 0.25
+    want = ct_oracle.ct_loss(o1, o2, yhn, forget, batch.n_id.cpu(), data.clean)
+    want[0].backward()
+    want[1].backward()
+    ct = CoTeachingTrainer(nets[0], nets[1], lr=1e-3)
+    before = [t.buckets.param.clone() for t in (ct.t1, ct.t2)]
+    ct.train_step(batch, forget, clean_attr="clean")
+    st = ct.read_stats()
+    assert abs(st[0] - float(want[0])) < 1e-5 * max(1.0, abs(float(want[0])))
+    assert abs(st[1] - float(want[1])) < 1e-5 * max(1.0, abs(float(want[1])))
+    assert abs(st[4] - float(want[2])) < 1e-6 and abs(st[5] - float(want[3])) < 1e-6
+    y = batch.y[:bs].view(-1).cpu()
+    assert int(st[2]) == int((o1.argmax(-1) == y).sum()) and int(st[3]) == int((o2.argmax(-1) == y).sum())
+    for net, ref in zip(nets, refs):
+        for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            assert rel_err(p.grad, q.grad) < 2e-5, k
+    for t, b in zip((ct.t1, ct.t2), before):
+        assert not torch.equal(t.buckets.param, b)

@@ -124,3 +124,22 @@ def test_dropout_mask_rate():
     m = philox.dropout_keep_mask(512, 256, 0.5, seed=1232, offset=9)
     assert abs(m.mean() - 0.5) < 0.01
     assert philox.dropout_keep_mask(8, 7, 0.0, 1, 1).all()
+
+
+def test_gcnconv_oracle_hand_computed():
+    """GCNConv(normalize=False) on a 4-node graph worked by hand: sum over in-neighbours of x W^T, + bias; node 3 has
+    no in-edge (=> bias only); edge (0 -> 1) is duplicated and counts twice; the self loop (2 -> 2) is an ordinary edge."""
+    import torch
+    from oracle import sage_oracle
+    conv = sage_oracle.GCNConvRef(2, 2, dtype=torch.float64)
+    with torch.no_grad():
+        conv.lin.weight.copy_(torch.tensor([[1.0, 2.0], [0.5, -1.0]], dtype=torch.float64))
+        conv.bias.copy_(torch.tensor([0.25, -0.5], dtype=torch.float64))
+    x = torch.tensor([[1.0, 0.0], [0.0, 1.0], [2.0, 1.0], [3.0, 3.0]], dtype=torch.float64)
+    ei = torch.tensor([[0, 0, 2, 1, 3], [1, 1, 2, 0, 0]])
+    z = [[1.0, 0.5], [2.0, -1.0], [4.0, 0.0], [9.0, -1.5]]                 # x W^T
+    want = [[z[1][0] + z[3][0] + 0.25, z[1][1] + z[3][1] - 0.5],           # node 0 <- 1, 3
+            [2 * z[0][0] + 0.25, 2 * z[0][1] - 0.5],                       # node 1 <- 0 twice
+            [z[2][0] + 0.25, z[2][1] - 0.5],                               # node 2 <- itself
+            [0.25, -0.5]]                                                  # node 3: no in-edge
+    assert torch.equal(conv(x, ei), torch.tensor(want, dtype=torch.float64))
