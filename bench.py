@@ -119,7 +119,8 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner (NCCL_DEBUG >= VERSION) to stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
     assert lib.ngnn_device_supported() == 1, "libngnn_b200.so is sm_100a only"
