@@ -42,85 +42,158 @@ __device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x;
 #include "agg_bulk.cuh"   // k_agg_fwd_bulk: rows staged through shared memory by the async copy engines
 namespace ngnn {
 
+// Gather-accumulate of the neighbours [beg, end) of one output row into acc (columns c0 + gl + v*G), U rows in flight.
+template <int G, int VPL, int U>
+__device__ __forceinline__ void seg_accumulate(const AggParams& p, int beg, int end, int c0, int F4, int gl, unsigned gmask,
+                                               float4 (&acc)[VPL]) {
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = beg; base < end; base += G) {
+    const int cnt = min(G, end - base);
+    const int my = (gl < cnt) ? __ldg(p.idx + base + gl) : 0;
+    for (int j = 0; j < cnt; j += U) {
+      // up to U neighbour rows in flight; out-of-range slots are masked
+      float4 v4[U][VPL];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int su = __shfl_sync(gmask, my, min(j + u, cnt - 1), G);
+        const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)su * p.ld_x);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = c0 + gl + v * G;
+          v4[u][v] = (c < F4 && j + u < cnt) ? ldg_nc_f4(src + c) : zero4;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) f4_add(acc[v], v4[u][v]);
+    }
+  }
+}
+
+// scale, bias, add row, gate, store of one finished column chunk of `row`.  PRE: the gate / add rows were requested
+// before the gather (narrow rows: the registers are there); otherwise they are loaded here.
+template <int G, int VPL, bool PRE>
+__device__ __forceinline__ void seg_finish(const AggParams& p, int64_t row, int c0, int F4, int gl, float scale, bool has_add,
+                                           const float4 (&acc)[VPL], const float4 (&gate)[PRE ? VPL : 1],
+                                           const float4 (&addv)[PRE ? VPL : 1]) {
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int c = c0 + gl + v * G;
+    if (c >= F4) continue;
+    float4 r = acc[v];
+    r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+    if (p.bias != nullptr) f4_add(r, __ldg(reinterpret_cast<const float4*>(p.bias) + c));
+    if (has_add) f4_add(r, PRE ? addv[PRE ? v : 0] : ldg_nc_f4(reinterpret_cast<const float4*>(p.add + row * p.ld_add) + c));
+    if (p.act_ref != nullptr) {
+      const float4 h = PRE ? gate[PRE ? v : 0] : ldg_nc_f4(reinterpret_cast<const float4*>(p.act_ref + row * p.ld_act) + c);
+      r.x = h.x > 0.f ? r.x * p.act_scale : 0.f;
+      r.y = h.y > 0.f ? r.y * p.act_scale : 0.f;
+      r.z = h.z > 0.f ? r.z * p.act_scale : 0.f;
+      r.w = h.w > 0.f ? r.w * p.act_scale : 0.f;
+    }
+    reinterpret_cast<float4*>(p.out + row * p.ld_out)[c] = r;
+  }
+}
+
 // Generic one-row-per-group kernel (all widths, optional add / gate / root gather).  U = neighbour rows in flight.
+// G == 32 only: rows longer than kLongRow (hubs of a power-law graph: un-sampled convolutions, the transposed blocks of
+// the backward) are not walked by their one warp — the CTA's warps each reduce a contiguous slice of the row and the
+// slices are combined through shared memory in warp order (still atomic-free and run-to-run deterministic).
+constexpr int kLongRow = 1024;
+constexpr int kLongWarps = 8;
 template <int G, int VPL, int U>
 __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
   constexpr int GROUPS_PER_WARP = 32 / G;
+  constexpr bool COOP = (G == 32);
+  // VPL == 4 (F 260..512): the 2 x VPL float4 of prefetch registers drop the kernel from 3 to 2 CTAs per SM (measured
+  // 2.5x slower on the C5 sweep); VPL == 8 is at 2 CTAs per SM either way and measured faster with the prefetch.
+  constexpr bool PRE = (VPL != 4);
+  constexpr int NPRE = PRE ? VPL : 1;
+  __shared__ float4 s_part[COOP ? kLongWarps : 1][COOP ? VPL * 32 : 1];
+  __shared__ int s_long[16];
+  __shared__ int s_nlong;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);                 // lane within group
   const int gw = lane / G;                       // group within warp
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gw * G));
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t row = warp * GROUPS_PER_WARP + gw;
-  if (row >= p.n_rows) return;
+  const bool valid = row < p.n_rows;
+  if (!COOP && !valid) return;
+  if (COOP) {
+    if (threadIdx.x == 0) s_nlong = 0;
+    __syncthreads();
+  }
 
   const int F4 = (int)(p.F >> 2);
-  // The extents and the indices are two small arrays read strictly in row order, so without help every CTA pays two
-  // compulsory DRAM misses IN SERIES before its first feature row moves (ncu, layer-2 backward: 6,300 cycles per row,
-  // DRAM 28 %).  Each group asks L2 for the sectors the rows kPrefetchRows further on will need.
-  constexpr int64_t kPrefetchRows = 16384;
-  const int e_total = __ldg(p.ptr + p.n_rows);
-  if (gl == 0 && row + kPrefetchRows <= p.n_rows) prefetch_l2(p.ptr + row + kPrefetchRows);
-  const int beg = __ldg(p.ptr + row), end = __ldg(p.ptr + row + 1);
-  if (gl == 0 && (int64_t)beg + kPrefetchRows < e_total) prefetch_l2(p.idx + beg + kPrefetchRows);
-  const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
-  const bool has_add = p.add != nullptr && row < p.n_add;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  for (int c0 = 0; c0 < F4; c0 += G * VPL) {
-    float4 acc[VPL];
+  int beg = 0, end = 0;
+  if (valid) {
+    // The extents and the indices are two small arrays read strictly in row order: each group asks L2 for the sectors
+    // the rows kPrefetchRows further on will need.
+    constexpr int64_t kPrefetchRows = 16384;
+    const int e_total = __ldg(p.ptr + p.n_rows);
+    if (gl == 0 && row + kPrefetchRows <= p.n_rows) prefetch_l2(p.ptr + row + kPrefetchRows);
+    beg = __ldg(p.ptr + row); end = __ldg(p.ptr + row + 1);
+    if (gl == 0 && (int64_t)beg + kPrefetchRows < e_total) prefetch_l2(p.idx + beg + kPrefetchRows);
+  }
+  const bool is_long = COOP && valid && (end - beg) > kLongRow;
+  if (valid && !is_long) {
+    const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
+    const bool has_add = p.add != nullptr && row < p.n_add;
+    for (int c0 = 0; c0 < F4; c0 += G * VPL) {
+      float4 acc[VPL];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) acc[v] = zero4;
-    // the gate / add rows of THIS output row do not depend on the extents -> indices -> rows chain: request them
-    // first so their DRAM latency runs under it (backward: 2 of the 3 streams of the kernel)
-    float4 gate[VPL], addv[VPL];
+      for (int v = 0; v < VPL; ++v) acc[v] = zero4;
+      // the gate / add rows of THIS output row do not depend on the extents -> indices -> rows chain: request them
+      // first so their DRAM latency runs under it (backward: 2 of the 3 streams of the kernel)
+      float4 gate[NPRE], addv[NPRE];
+      if (PRE) {
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int c = c0 + gl + v * G;
-      gate[v] = (p.act_ref != nullptr && c < F4) ? ldg_nc_f4(reinterpret_cast<const float4*>(p.act_ref + row * p.ld_act) + c) : zero4;
-      addv[v] = (has_add && c < F4) ? ldg_nc_f4(reinterpret_cast<const float4*>(p.add + row * p.ld_add) + c) : zero4;
-    }
-
-    for (int base = beg; base < end; base += G) {
-      const int cnt = min(G, end - base);
-      const int my = (gl < cnt) ? __ldg(p.idx + base + gl) : 0;
-      for (int j = 0; j < cnt; j += U) {
-        // up to U neighbour rows in flight; out-of-range slots are masked
-        float4 v4[U][VPL];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int su = __shfl_sync(gmask, my, min(j + u, cnt - 1), G);
-          const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)su * p.ld_x);
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            const int c = c0 + gl + v * G;
-            v4[u][v] = (c < F4 && j + u < cnt) ? ldg_nc_f4(src + c) : zero4;
-          }
+        for (int v = 0; v < NPRE; ++v) {
+          const int c = c0 + gl + v * G;
+          gate[v] = (p.act_ref != nullptr && c < F4) ? ldg_nc_f4(reinterpret_cast<const float4*>(p.act_ref + row * p.ld_act) + c) : zero4;
+          addv[v] = (has_add && c < F4) ? ldg_nc_f4(reinterpret_cast<const float4*>(p.add + row * p.ld_add) + c) : zero4;
         }
+      }
+      seg_accumulate<G, VPL, U>(p, beg, end, c0, F4, gl, gmask, acc);
+      seg_finish<G, VPL, PRE>(p, row, c0, F4, gl, scale, has_add, acc, gate, addv);
+    }
+  }
+  if (COOP) {
+    const int wib = threadIdx.x >> 5, nw = min((int)(blockDim.x >> 5), kLongWarps);
+    if (is_long && lane == 0) s_long[atomicAdd(&s_nlong, 1)] = wib;       // list order is irrelevant to each row's result
+    __syncthreads();
+    const int nlong = s_nlong;                                            // CTA-uniform
+    for (int k = 0; k < nlong; ++k) {
+      const int64_t lrow = (int64_t)blockIdx.x * (blockDim.x >> 5) + s_long[k];
+      const int lbeg = __ldg(p.ptr + lrow), lend = __ldg(p.ptr + lrow + 1);
+      const int slice = ((lend - lbeg + nw - 1) / nw + 31) & ~31;          // whole 32-index windows per warp
+      const int sb = min(lend, lbeg + wib * slice), se = wib < nw ? min(lend, sb + slice) : sb;
+      const float scale = p.mean ? 1.0f / (float)max(lend - lbeg, 1) : 1.0f;
+      const bool has_add = p.add != nullptr && lrow < p.n_add;
+      for (int c0 = 0; c0 < F4; c0 += 32 * VPL) {
+        float4 acc[VPL];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int v = 0; v < VPL; ++v) acc[v] = zero4;
+        seg_accumulate<G, VPL, U>(p, sb, se, c0, F4, lane, 0xffffffffu, acc);
+        if (wib < nw) {
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) f4_add(acc[v], v4[u][v]);
+          for (int v = 0; v < VPL; ++v) s_part[wib][v * 32 + lane] = acc[v];
+        }
+        __syncthreads();
+        if (wib == 0) {
+          const float4 none[1] = {zero4};
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            for (int w = 1; w < nw; ++w) f4_add(acc[v], s_part[w][v * 32 + lane]);     // fixed warp order
+          seg_finish<G, VPL, false>(p, lrow, c0, F4, lane, scale, has_add, acc, none, none);
+        }
+        __syncthreads();
       }
     }
-
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int c = c0 + gl + v * G;
-      if (c >= F4) continue;
-      float4 r = acc[v];
-      r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
-      if (p.bias != nullptr) f4_add(r, __ldg(reinterpret_cast<const float4*>(p.bias) + c));
-      if (has_add) f4_add(r, addv[v]);
-      if (p.act_ref != nullptr) {
-        const float4 h = gate[v];
-        r.x = h.x > 0.f ? r.x * p.act_scale : 0.f;
-        r.y = h.y > 0.f ? r.y * p.act_scale : 0.f;
-        r.z = h.z > 0.f ? r.z * p.act_scale : 0.f;
-        r.w = h.w > 0.f ? r.w * p.act_scale : 0.f;
-      }
-      reinterpret_cast<float4*>(p.out + row * p.ld_out)[c] = r;
-    }
+    if (!valid) return;
   }
   if (p.root_idx != nullptr) {
     const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)__ldg(p.root_idx + row) * p.ld_x);

@@ -162,6 +162,45 @@ def test_agg_bwd_matches_oracle(dev, F):
     assert rel_err(got2, want_gated) < RTOL
 
 
+@pytest.mark.parametrize("F", [64, 100, 256, 512, 1024])
+def test_agg_hub_rows_are_split_across_the_cta(dev, F):
+    """Rows far longer than kLongRow (power-law hubs: un-sampled convolutions, transposed blocks) — the generic kernel's
+    CTA-cooperative path: forward with the GCN bias (sum), backward with add rows and gate; against the oracle within the
+    fp32 summation-order tolerance, and bitwise reproducible run to run."""
+    from noise_gnn_b200 import ops
+    n = 700
+    g = torch.Generator().manual_seed(F)
+    hubs = {3: 5000, 4: 1025, 250: 2500, 699: 3333}        # several per CTA (rows 3, 4) and the last row
+    deg = torch.randint(0, 12, (n,), generator=g)
+    for r, d in hubs.items():
+        deg[r] = d
+    dst = torch.repeat_interleave(torch.arange(n), deg)
+    src = torch.randint(0, n, (dst.numel(),), generator=g)
+    ei = torch.stack([src, dst])
+    x = torch.randn(n, F, generator=g)
+    bias = torch.randn(F, generator=g)
+    blk = ops.coo_to_csr(ei.to(dev), n)
+    # forward, sum + bias (GCN propagation; always the generic kernel)
+    msg = x.double().index_select(0, src)
+    want = torch.zeros(n, F, dtype=torch.float64).index_add_(0, dst, msg) + bias.double()
+    ref32 = torch.zeros(n, F).index_add_(0, dst, x.index_select(0, src)) + bias
+    tol = max(RTOL, 4 * rel_err(ref32, want))
+    a = ops.gcn_agg_fwd(blk.rowptr, blk.col, x.to(dev), n, bias=bias.to(dev))
+    b = ops.gcn_agg_fwd(blk.rowptr, blk.col, x.to(dev), n, bias=bias.to(dev))
+    assert torch.equal(a, b), "not bitwise reproducible"
+    assert rel_err(a, want) < tol
+    # backward form on the same structure: add rows on a prefix + gate
+    add = torch.randn(300, F, generator=g)
+    h = torch.randn(n, F, generator=g)
+    want_b = torch.zeros(n, F, dtype=torch.float64).index_add_(0, dst, msg)
+    want_b[:300] += add.double()
+    want_b = torch.where(h > 0, want_b * 2.0, torch.zeros_like(want_b))
+    c = ops.agg_bwd(blk.rowptr, blk.col, x.to(dev), n, dx_root=add.to(dev), n_root=300, act_ref=h.to(dev), act_scale=2.0)
+    d = ops.agg_bwd(blk.rowptr, blk.col, x.to(dev), n, dx_root=add.to(dev), n_root=300, act_ref=h.to(dev), act_scale=2.0)
+    assert torch.equal(c, d)
+    assert rel_err(c, want_b) < tol
+
+
 # ------------------------------------------------------------------ K-GEMM / K-DGRAD / K-WGRAD
 GEMM_SHAPES = [(1, 4, 3), (130, 100, 256), (700, 256, 47), (257, 128, 40), (300, 1433, 7), (90, 767, 10),
                (1000, 500, 3), (513, 256, 256), (64, 512, 7), (300, 64, 512), (4000, 100, 256)]
