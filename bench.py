@@ -124,6 +124,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
     assert lib.ngnn_device_supported() == 1, "libngnn_b200.so is sm_100a only"
+    for kv in filter(None, os.environ.get("NGNN_TUNING", "").split(",")):      # A/B switches, e.g. NGNN_TUNING=7:0
+        k, v = kv.split(":")
+        _lib.call("ngnn_set_tuning", int(k), int(v))
 
     t_setup = time.time()
     data, sh, train_idx = build_problem(args, device)

@@ -208,6 +208,13 @@ int32_t ngnn_sample_block(const int32_t* colptr, const int32_t* row, int64_t N,
                           int32_t* n_id, int32_t* rowptr, int32_t* col, int32_t* col_global, int32_t* e_pos,
                           int32_t* counts, void* ws, size_t ws_bytes, ngnn_stream_t stream);
 
+/* Table rows of a sampled block for a feature table stored in another row order (remap[global id] = table row, int32 [N]):
+ * col_table[p] = remap[col_global[p]] for p < e, n_table[i] = remap[n_id[i]] for i < n, with n / e read from the
+ * sampler's device-side `counts` (no host round trip; grids sized by max_nodes / max_edges).                     */
+int32_t ngnn_block_table_index(const int32_t* remap, const int32_t* col_global, const int32_t* n_id,
+                               const int32_t* counts, int32_t H, int64_t max_nodes, int64_t max_edges,
+                               int32_t* col_table, int32_t* n_table, ngnn_stream_t stream);
+
 /* ---- the whole step behind one call (loop body of PipelineCO.train, reference src/pipeline.py:152-168) ----
  * SAGE network of reference src/models/layers/sage.py:7-40: num_layers SAGEConv layers
  * (in_dim -> hidden_dim -> ... -> out_dim), ReLU + dropout between layers.  Parameters and gradients live in flat
@@ -234,6 +241,12 @@ typedef struct {
    * builds them on its side stream so the sort is off the step's critical path.                           */
   const int32_t* colptr_t[8];
   const int32_t* row_t[8];
+  /* Optional feature-table addressing (ngnn_block_table_index): when the resident table is stored hot rows first,
+   * col_table[p] / n_table[i] are the TABLE rows of col_global[p] / n_id[i] and rows < hot_rows are the hot set
+   * (L2 evict_last priority; the others stream through with evict_first).  NULL / 0: the table is indexed by node id. */
+  const int32_t* col_table;
+  const int32_t* n_table;
+  int64_t        hot_rows;
 } ngnn_block_t;
 
 int64_t ngnn_sage_num_params(const ngnn_sage_model_t* model);

@@ -31,6 +31,8 @@ struct AggParams {
   int64_t ld_act;
   float act_scale;
   const float* bias;       // optional per-column bias added after the reduction (GCNConv: out = A_sum z + b)
+  int32_t keep_l2;         // table-mode gathers (root_idx != NULL) carry an L2 priority:
+  int64_t hot_rows;        //   < 0: every row evict_last; >= 0: rows < hot_rows evict_last, the others evict_first
   const int32_t* root_idx; // optional fused root gather (fwd): root[i] = x[root_idx[i]]
   float* root;
   int64_t ld_root;
@@ -269,6 +271,10 @@ __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
   const int F4 = (int)(p.F >> 2);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // ROOT = gathering from the resident feature table (layer 1): keep its rows in L2 ahead of the streaming activations
+  const bool keep = ROOT && p.keep_l2;
+  const uint64_t pol_hot = l2_policy_evict_last(), pol_cold = p.hot_rows >= 0 ? l2_policy_evict_first() : pol_hot;
+  const int64_t hot = p.hot_rows >= 0 ? p.hot_rows : INT64_MAX;
   int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t row1 = row0 + nwarps;
   int beg0 = 0, end0 = 0, rid0 = 0, beg1 = 0, end1 = 0, rid1 = 0, my0 = 0;
@@ -291,7 +297,8 @@ __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
     for (int v = 0; v < VPL; ++v) {
       const int c = lane + v * 32;
       acc[v] = zero4;
-      rootv[v] = (ROOT && c < F4) ? ldg_nc_f4(reinterpret_cast<const float4*>(p.x + (int64_t)rid0 * p.ld_x) + c) : zero4;
+      rootv[v] = (ROOT && c < F4) ? (keep ? ldg_nc_f4_hint(reinterpret_cast<const float4*>(p.x + (int64_t)rid0 * p.ld_x) + c, rid0 < hot ? pol_hot : pol_cold)
+                                          : ldg_nc_f4(reinterpret_cast<const float4*>(p.x + (int64_t)rid0 * p.ld_x) + c)) : zero4;
     }
     int my = my0;
     for (int base = beg0; base < end0; base += 32) {
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             const int c = lane + v * 32;
-            v4[u][v] = (c < F4 && j + u < cnt) ? ldg_nc_f4(src + c) : zero4;
+            v4[u][v] = (c < F4 && j + u < cnt) ? (keep ? ldg_nc_f4_hint(src + c, su < hot ? pol_hot : pol_cold) : ldg_nc_f4(src + c)) : zero4;
           }
         }
 #pragma unroll
@@ -351,6 +358,7 @@ static int g_tune_unroll = 0;    // ngnn_set_tuning(0, u): 0 = default, else for
 static int g_tune_threads = 256; // ngnn_set_tuning(1, t): CTA size 128 / 256 / 512
 static int g_tune_pipe = 1;      // ngnn_set_tuning(3, 0/1): software-pipelined persistent forward kernel
 static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 < F <= 128 (32 / 16 / 8)
+static int g_tune_keep = 1;      // ngnn_set_tuning(7, 0|1): L2 evict_last priority on the layer-1 table gathers
 static int g_tune_bulk = 0;      // ngnn_set_tuning(5, v): 0 = off, else 100*mode + 10*chunk_sel + stage_sel (see launch_bulk)
 
 template <int CH, int S, int MODE, bool ROOT>
@@ -451,6 +459,23 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
 
 }  // namespace ngnn
 
+namespace ngnn {
+int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, int64_t n_dst,
+                           int64_t F, float* mean, int64_t ld_mean, const int32_t* root_table, float* root, int64_t ld_root,
+                           int64_t hot_rows, cudaStream_t st) {
+  if (n_dst == 0 || F == 0) return NGNN_OK;
+  NGNN_REQUIRE(rowptr && table && mean && ld_table >= F && ld_mean >= F, NGNN_E_INVALID, "agg_fwd_table: bad arguments");
+  // (Measured, round 1: reserving an L2 persisting set-aside for the hot rows — cudaLimitPersistingL2CacheSize — made this
+  //  kernel slower, 57 us vs 52 us with the plain cache hints, so no device-wide limit is touched.)
+  AggParams p{};
+  p.ptr = rowptr; p.idx = col_table; p.x = table; p.ld_x = ld_table; p.n_rows = n_dst; p.F = F;
+  p.out = mean; p.ld_out = ld_mean; p.mean = 1;
+  p.root_idx = root_table; p.root = root; p.ld_root = ld_root;
+  p.keep_l2 = g_tune_keep; p.hot_rows = hot_rows;
+  return run_agg(p, st);
+}
+}  // namespace ngnn
+
 using namespace ngnn;
 
 extern "C" int32_t ngnn_set_gemm_tile(int32_t bn_max);   // gemm.cu
@@ -466,6 +491,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 4 && (value == 128 || value == 256)) return ngnn_set_gemm_tile(value);
   if (key == 5 && value >= 0 && value < 300) { g_tune_bulk = value; return NGNN_OK; }
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
+  if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);
 }
 
@@ -481,6 +507,7 @@ int32_t ngnn_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const float
   p.ptr = rowptr; p.idx = col; p.x = x; p.ld_x = ld_x; p.n_rows = n_dst; p.F = F;
   p.out = mean; p.ld_out = ld_mean; p.mean = 1;
   p.root_idx = root_idx; p.root = root; p.ld_root = ld_root;
+  p.keep_l2 = g_tune_keep; p.hot_rows = -1;
   return run_agg(p, as_stream(stream));
 }
 

@@ -50,6 +50,11 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 //   mode 0: forward pack [W_l | W_r] (K-major) -> ws of ngnn_sage_gemm_workspace_bytes(F, O)
 //   mode 1: data-gradient pack [W_l^T ; W_r^T]  -> ws of ngnn_sage_dgrad_workspace_bytes(F, O)
 // Returns NGNN_E_UNSUPPORTED when the shape takes the SIMT kernels (which read the weights directly).
+// K-AGG forward from the resident feature table with a hot-row split (agg.cu): table rows < hot_rows are gathered with
+// L2 evict_last priority, the rest with evict_first (hot_rows < 0: every row evict_last).
+int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, int64_t n_dst,
+                           int64_t F, float* mean, int64_t ld_mean, const int32_t* root_table, float* root, int64_t ld_root,
+                           int64_t hot_rows, cudaStream_t st);
 int32_t prep_weights_impl(int32_t mode, const float* w_l, const float* w_r, int64_t F, int64_t O, void* ws, size_t ws_bytes,
                           cudaStream_t st);
 // Batched form: prep_batch_add collects jobs (same arguments / return codes), prep_batch_launch runs them in one launch.
@@ -98,6 +103,26 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// Same with an L2 evict_last priority: rows of the resident feature table.  Hub nodes of a power-law graph are gathered
+// again and again (within a block and from step to step); at default priority the step's streaming activations
+// (~0.5 GB per step through a 126 MB L2) push them out between uses.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_nc_f4_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 }
 

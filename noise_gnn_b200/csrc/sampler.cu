@@ -263,11 +263,34 @@ __global__ void k_finish(const int32_t* __restrict__ counts, int32_t H, const in
   local_of[n_id[i]] = -1;
 }
 
+// Feature-table addresses of a block: the table may be stored in a different row order than the node ids (hot rows
+// first, see NeighborLoader(hot_feature_rows=...)); remap[global id] = table row.
+__global__ void k_table_index(const int32_t* __restrict__ remap, const int32_t* __restrict__ col_global,
+                              const int32_t* __restrict__ n_id, const int32_t* __restrict__ counts, int32_t H,
+                              int32_t* __restrict__ col_table, int32_t* __restrict__ n_table) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int32_t n = counts[H], e = counts[2 * H + 1];
+  if (i < e) col_table[i] = __ldg(remap + col_global[i]);
+  if (i < n) n_table[i] = __ldg(remap + n_id[i]);
+}
+
 }  // namespace ngnn
 
 using namespace ngnn;
 
 extern "C" {
+
+int32_t ngnn_block_table_index(const int32_t* remap, const int32_t* col_global, const int32_t* n_id, const int32_t* counts,
+                               int32_t H, int64_t max_nodes, int64_t max_edges, int32_t* col_table, int32_t* n_table,
+                               ngnn_stream_t stream) {
+  NGNN_REQUIRE(remap && col_global && n_id && counts && col_table && n_table, NGNN_E_INVALID, "block_table_index: null pointer");
+  NGNN_REQUIRE(H >= 1 && max_nodes >= 0 && max_edges >= 0, NGNN_E_INVALID, "block_table_index: bad sizes");
+  const int64_t m = max_nodes > max_edges ? max_nodes : max_edges;
+  if (m == 0) return NGNN_OK;
+  k_table_index<<<(unsigned)ceil_div(m, 256), 256, 0, as_stream(stream)>>>(remap, col_global, n_id, counts, H, col_table, n_table);
+  NGNN_LAUNCH_CHECK();
+  return NGNN_OK;
+}
 
 int32_t ngnn_sample_capacity(int32_t bs, const int32_t* fanouts, int32_t H, int64_t N, int64_t* max_nodes,
                              int64_t* max_edges) {

@@ -214,8 +214,10 @@ static int32_t sage_step_impl(const ngnn_sage_model_t* model, const float* param
     if (i == 0) {   // aggregate from the resident table by global ids; gather the root rows in the same launch
       const bool probe = g_probe_n < g_probe_cap;
       if (probe) cudaEventRecord(g_probe_ev[2 * g_probe_n], as_stream(stream));
-      rc = ngnn_sage_agg_fwd(block->rowptr, block->col_global, table, ld_table, lp.n_dst, lp.F, F32(lp.mean), lp.F, block->n_id,
-                             F32(lp.root), lp.F, stream);
+      const bool remapped = block->col_table != nullptr && block->n_table != nullptr;      // table stored hot rows first
+      rc = agg_fwd_table_impl(block->rowptr, remapped ? block->col_table : block->col_global, table, ld_table, lp.n_dst, lp.F,
+                              F32(lp.mean), lp.F, remapped ? block->n_table : block->n_id, F32(lp.root), lp.F,
+                              remapped ? block->hot_rows : -1, as_stream(stream));
       if (probe) { cudaEventRecord(g_probe_ev[2 * g_probe_n + 1], as_stream(stream)); ++g_probe_n; }
       root = F32(lp.root); ld_root = lp.F;
     } else {

@@ -109,6 +109,7 @@ class Block:
         self.n_cols = int(n_cols if n_cols is not None else n_rows)
         self.hop_nodes, self.hop_edges = hop_nodes, hop_edges
         self.col_global, self.n_id = col_global, n_id
+        self.col_table = self.n_table = None      # table rows of col_global / n_id when the loader keeps a hot-rows-first table
         self._t = {}
 
     def transpose(self, e_limit: Optional[int] = None, n_cols: Optional[int] = None):

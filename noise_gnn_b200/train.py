@@ -125,6 +125,15 @@ class Trainer:
         return _lib.SageModel(self._cfg["num_layers"], self._cfg["in_dim"], self._cfg["hidden_dim"], self._cfg["out_dim"],
                               float(m.dropout), int(training))
 
+    @staticmethod
+    def _table(loader, blk, bd):
+        """Feature table the layer-1 gather reads: the loader's hot-rows-first copy when the block carries its table
+        rows (col_table / n_table), else the table in node-id order."""
+        if loader.x_hot is not None and blk.col_table is not None and blk.n_table is not None:
+            bd.col_table, bd.n_table, bd.hot_rows = blk.col_table.data_ptr(), blk.n_table.data_ptr(), loader.hot_rows
+            return loader.x_hot
+        return loader.x
+
     def _ensure_arena(self, loader, ms):
         key = (loader.batch_size, tuple(loader.num_neighbors), loader.num_nodes)
         if self._arena_key != key:
@@ -159,6 +168,7 @@ class Trainer:
                     bd.colptr_t[b], bd.row_t[b] = pre[0].data_ptr(), pre[1].data_ptr()
         tgt = loader.label_array(target_attr) if target_attr else None
         lab = loader.label_array(label_attr) if label_attr else None
+        table = self._table(loader, blk, bd)
         logits = None
         if want_logits:
             logits = torch.empty((batch.batch_size, self._cfg["out_dim"]), dtype=torch.float32, device=arena.device)
@@ -166,7 +176,7 @@ class Trainer:
         with ops._timed("sage_step"):
             _lib.call("ngnn_sage_step", ctypes.byref(ms), ops._ptr(self.buckets.param),
                       ops._ptr(self.buckets.grad) if train else None, ctypes.byref(bd), self._max_nodes, self._max_edges,
-                      ops._ptr(loader.x), loader.x.stride(0), ops._ptr(tgt), ops._ptr(lab), self.model.drop_seed,
+                      ops._ptr(table), table.stride(0), ops._ptr(tgt), ops._ptr(lab), self.model.drop_seed,
                       self.steps * self._cfg["num_layers"], ops._ptr(self.stats), ops._ptr(logits),
                       logits.stride(0) if logits is not None else 0, ops._ptr(arena), arena.numel(), ops._stream())
         return logits
@@ -209,9 +219,10 @@ class Trainer:
         arena = self._ensure_arena(loader, ms)
         bd, keep = self._block_desc(batch)
         logits = torch.empty((batch.batch_size, self._cfg["out_dim"]), dtype=torch.float32, device=arena.device)
+        table = self._table(loader, batch.block, bd)
         self.steps += 1
         _lib.call("ngnn_sage_forward", ctypes.byref(ms), ops._ptr(self.buckets.param), ctypes.byref(bd), self._max_nodes,
-                  self._max_edges, ops._ptr(loader.x), loader.x.stride(0), self.model.drop_seed,
+                  self._max_edges, ops._ptr(table), table.stride(0), self.model.drop_seed,
                   self.steps * self._cfg["num_layers"], ops._ptr(logits), logits.stride(0), ops._ptr(arena), arena.numel(),
                   ops._stream())
         return logits
@@ -223,8 +234,9 @@ class Trainer:
         arena = self._ensure_arena(loader, ms)
         bd, keep = self._block_desc(batch)
         dlogits = ops._rows(dlogits, "dlogits")
+        table = self._table(loader, batch.block, bd)
         _lib.call("ngnn_sage_backward", ctypes.byref(ms), ops._ptr(self.buckets.param), ops._ptr(self.buckets.grad),
-                  ctypes.byref(bd), self._max_nodes, self._max_edges, ops._ptr(loader.x), loader.x.stride(0),
+                  ctypes.byref(bd), self._max_nodes, self._max_edges, ops._ptr(table), table.stride(0),
                   ops._ptr(dlogits), ops._ld(dlogits), ops._ptr(arena), arena.numel(), ops._stream())
 
     # ------------------------------------------------------------------ autograd variant (same kernels, ~80 FFI calls)

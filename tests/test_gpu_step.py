@@ -230,3 +230,36 @@ def test_coteaching_step_matches_oracle(dev):
             assert rel_err(p.grad, q.grad) < 2e-5, k
     for t, b in zip((ct.t1, ct.t2), before):
         assert not torch.equal(t.buckets.param, b)
+
+
+def test_hot_rows_first_table_addresses_the_same_rows(dev):
+    """The loader's second, in-degree-sorted copy of the feature table and the per-block table indices: x_hot[remap[g]]
+    is row g, (col_table, n_table) are remap of (col_global, n_id), the hot prefix holds the highest-degree nodes, and
+    the fused step gives the same loss / gradients with and without it (bitwise: same rows, same order)."""
+    from noise_gnn_b200 import NeighborLoader, SAGE
+    from noise_gnn_b200.synthetic import make_dataset
+    from noise_gnn_b200.train import Trainer
+    data, sh, train_idx = make_dataset("arxiv", scale=0.05, device="cpu", noise_type="sym", noise_rate=0.3)
+    kw = dict(input_nodes=train_idx, num_neighbors=[10, 5], batch_size=128, shuffle=True, seed=1232)
+    hot = NeighborLoader(data, hot_feature_bytes=64 * 1024, **kw)
+    plain = NeighborLoader(data, hot_feature_bytes=0, **kw)
+    assert plain.x_hot is None and hot.x_hot is not None and 0 < hot.hot_rows < data.num_nodes
+    remap = hot.remap.long()
+    assert torch.equal(torch.sort(remap).values, torch.arange(data.num_nodes, device=remap.device))
+    assert torch.equal(hot.x_hot[remap], hot.x)
+    deg = (hot.colptr[1:] - hot.colptr[:-1]).long()
+    inv = torch.empty_like(remap); inv[remap] = torch.arange(data.num_nodes, device=remap.device)
+    assert bool((deg[inv][:-1] >= deg[inv][1:]).all())                   # table order = descending in-degree
+    bh, bp = next(iter(hot)), next(iter(plain))
+    assert torch.equal(bh.block.col_global, bp.block.col_global) and torch.equal(bh.block.n_id, bp.block.n_id)
+    assert torch.equal(bh.block.col_table.long(), remap[bh.block.col_global.long()])
+    assert torch.equal(bh.block.n_table.long(), remap[bh.block.n_id.long()])
+    assert bp.block.col_table is None
+    grads, losses = [], []
+    for batch in (bh, bp):
+        torch.manual_seed(7)
+        net = SAGE(sh.features, 64, sh.classes, 3, dropout=0.0).to(dev)
+        tr = Trainer(net, lr=1e-3)
+        tr.forward_backward(batch)
+        grads.append(tr.buckets.grad.clone()); losses.append(tr.read_stats()[0])
+    assert losses[0] == losses[1] and torch.equal(grads[0], grads[1])
