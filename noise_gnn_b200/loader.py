@@ -218,6 +218,7 @@ class NeighborLoader:
             # --- sampler capacities and workspace ---
             L = _lib.load()
             self._fan = (ctypes.c_int32 * len(self.num_neighbors))(*self.num_neighbors)
+            self._fan_cap = (ctypes.c_int32 * len(self.num_neighbors))(*self.num_neighbors)
             mn, me = ctypes.c_int64(), ctypes.c_int64()
             _lib.call("ngnn_sample_capacity", self.batch_size, self._fan, len(self.num_neighbors), N,
                       ctypes.byref(mn), ctypes.byref(me))
@@ -225,6 +226,16 @@ class NeighborLoader:
             nbytes = L.ngnn_sample_workspace_bytes(N, self.batch_size, self._fan, len(self.num_neighbors))
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             _lib.call("ngnn_sample_workspace_init", ops._ptr(self._ws), self._ws.numel(), N, ops._stream())
+
+    def set_num_neighbors(self, num_neighbors: Sequence[int]) -> None:
+        """Change the fan-outs between epochs.  Only prefixes / smaller fan-outs than the loader was built for are
+        accepted: the sampler workspace and block capacities were sized at construction."""
+        fan = [int(f) for f in num_neighbors]
+        cap = [int(self._fan_cap[i]) for i in range(len(self._fan_cap))]
+        if not fan or len(fan) > len(cap) or any(f < 1 or f > c for f, c in zip(fan, cap)):
+            raise ValueError(f"num_neighbors {fan} exceeds the capacity this loader was built with ({cap})")
+        self.num_neighbors = fan
+        self._fan = (ctypes.c_int32 * len(fan))(*fan)
 
     # ------------------------------------------------------------------ batching
     @property

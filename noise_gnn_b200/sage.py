@@ -141,21 +141,28 @@ class SAGE(torch.nn.Module):
     # ---- layer-wise inference (reference sage.py:42-58) -----------------------------------------
     @torch.no_grad()
     def inference(self, x_all, subgraph_loader, device=None, return_cpu: bool = True):
-        """Layer by layer over all input nodes of `subgraph_loader`, with the loader's sampled fan-outs
-        (as the reference does).  Activations stay on the GPU between layers; per batch only the seed
-        rows are computed (only hop-1 edges reach them)."""
+        """Layer by layer over all input nodes of `subgraph_loader`, with the loader's sampled fan-outs (as the reference
+        does: its eval loader keeps `num_neighbors`, pipeline.py:85-92).  Activations stay on the GPU between layers.
+        Per batch the reference runs one conv on the whole multi-hop block and keeps `[:batch_size]`; only the hop-1
+        edges reach those rows, and a node's hop-1 draws do not depend on the deeper hops (the sampler's RNG is keyed by
+        node and hop), so the loader is asked for hop 1 only and K-AGG gathers straight from the [N, F] activation table
+        by global id (no x[n_id] copy).  Seed-row outputs are the same function of the same sampled edges."""
         dev = subgraph_loader.device
         x_all = x_all.to(dev, dtype=torch.float32)
         last = self.num_layers - 1
-        for i, conv in enumerate(self.convs):
-            xs = []
-            for batch in subgraph_loader:
-                blk = batch.block
-                bs, e1 = batch.batch_size, blk.hop_edges[1]
-                x = ops.gather_rows(x_all, batch._n_id32, blk.hop_nodes[1])
-                mean = ops.agg_fwd(blk.rowptr, blk.col, x, bs)
-                out = ops.gemm_fwd(mean, x, conv.lin_l.weight, conv.lin_r.weight, conv.lin_l.bias, bs,
-                                   act=NGNN_ACT_RELU if i != last else NGNN_ACT_NONE)
-                xs.append(out)
-            x_all = torch.cat(xs, dim=0)
+        hops = list(subgraph_loader.num_neighbors)
+        subgraph_loader.set_num_neighbors(hops[:1])
+        try:
+            for i, conv in enumerate(self.convs):
+                xs = []
+                for batch in subgraph_loader:
+                    blk = batch.block
+                    bs = batch.batch_size
+                    mean, root = ops.agg_fwd(blk.rowptr, blk.col_global, x_all, bs, root_idx=blk.n_id)
+                    out = ops.gemm_fwd(mean, root, conv.lin_l.weight, conv.lin_r.weight, conv.lin_l.bias, bs,
+                                       act=NGNN_ACT_RELU if i != last else NGNN_ACT_NONE)
+                    xs.append(out)
+                x_all = torch.cat(xs, dim=0)
+        finally:
+            subgraph_loader.set_num_neighbors(hops)
         return x_all.cpu() if return_cpu else x_all
