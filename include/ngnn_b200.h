@@ -95,8 +95,12 @@ int32_t ngnn_gcn_agg_fwd(const int32_t* rowptr, const int32_t* col, const float*
                          int64_t n_dst, int64_t O, const float* bias, float* out, int64_t ld_out,
                          ngnn_stream_t stream);
 
-/* Development knob for kernel sweeps (profiles/prof_agg.py): key 0 = neighbour rows in flight per lane for
- * F <= 128 (2/4/8, 0 = default), key 1 = CTA size of the aggregation kernels (128/256/512).            */
+/* Development knobs for kernel sweeps and A/B measurements (profiles/prof_agg.py, profiles/prof_gemm.py, NGNN_TUNING in
+ * bench.py).  key 0: neighbour rows in flight per lane of K-AGG for F <= 128 (0 = default); 1: CTA size of the generic
+ * aggregation kernel (128/256/512); 2: lanes per row for 64 < F <= 128 (32/16/8); 3: software-pipelined persistent K-AGG
+ * (1 = default); 4: widest N tile of the tcgen05 GEMM (128 = default, 256); 5: shared-memory-staged K-AGG variant
+ * (0 = off, 100*(mode+1) + 10*chunk_sel + stages: mode 0 UBLKCP, 1 LDGSTS); 6: A operand of the tcgen05 kernels in
+ * tensor memory (1 = default) or shared memory (0); 7: L2 evict_last priority on the layer-1 table gathers (1 = default). */
 int32_t ngnn_set_tuning(int32_t key, int32_t value);
 
 /* ---- K-AGG-T: transpose (CSC) segment sum, backward of K-AGG ----

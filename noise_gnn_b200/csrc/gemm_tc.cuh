@@ -5,19 +5,23 @@
 // fp32-grade accuracy on the TF32 tensor pipe by the 3xTF32 split (SURVEY §7.3 hard part 1):
 //   x = hi + lo, hi = round-to-nearest of x to 10 mantissa bits, lo = x - hi (exact in fp32);
 //   D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo   (the dropped lo*lo term is ~2^-22 relative).
-// Weights (B) are split once per call by a tiny prep kernel into a packed K-major workspace
-// [rows, Kpack] (hi and lo planes, K zero-padded to whole 32-float blocks); activations (A) are
-// split in shared memory by the converter warps, in place, right after TMA lands them.
+// Weights (B) are split once per step (or per call) by a tiny prep kernel into a packed K-major workspace
+// [rows, Kpack] (hi and lo planes, K zero-padded to whole 32-float blocks); activations (A) are split by the
+// converter warps right after TMA lands them — into TENSOR MEMORY in the default TS form, into shared memory in the
+// SS form (kept for tiles wider than 128 columns and for A/B comparison, ngnn_set_tuning(6, 0)).
 //
-// One CTA = one 128 x BN output tile (BN = N rounded up to 16, <= 256), 6 warps:
-//   warp 0      TMA producer: per K-block (32 floats = one 128-byte swizzle atom) loads the raw A
-//               tile [128 x 32] and the B_hi / B_lo tiles [BN x 32] (SWIZZLE_128B) into a stage
-//   warp 1      allocates TMEM, issues tcgen05.mma.kind::tf32 (12 per K-block: 4 k-steps x 3 terms),
-//               tcgen05.commit frees the stage / signals the epilogue
-//   warps 2-5   converter (raw A -> hi in place, lo plane) during the main loop, then the epilogue:
-//               tcgen05.ld the fp32 accumulator, + bias, row scale, ReLU, Philox dropout, store.
-// Accumulators live in TMEM (128 lanes x BN fp32 columns).  Partial tiles rely on TMA's zero fill
-// for out-of-bounds rows / columns; stores are bounds-checked.
+// Persistent, warp-specialised, one CTA per SM, 128 x BN output tiles (BN = N rounded up to 16, <= 128 for TS), 14 warps:
+//   warp 0      TMA producer: per K-block (32 floats = one 128-byte swizzle atom) loads the raw A tile [128 x 32] and
+//               the B_hi / B_lo tiles [BN x 32] (SWIZZLE_128B) into a stage of the ring (4 stages of 48 KB at BN = 128)
+//   warp 1      allocates TMEM, issues tcgen05.mma.kind::tf32 (12 per K-block: 4 k-steps x 3 terms) with elect.sync and
+//               warp-uniform operands, waits on ONE mbarrier per K-block; tcgen05.commit frees the stage / signals the epilogue
+//   warps 2-5   converters: thread = tile row, raw A row -> hi / lo -> 64 TMEM columns of its lane (tcgen05.st)
+//   warps 6-13  epilogue (two per TMEM lane quarter): tcgen05.ld the fp32 accumulator, + bias, row scale, ReLU, Philox
+//               dropout (16 random bits per element), transposed through a shared-memory patch into full-line stores;
+//               two TMEM accumulator buffers let it run under the next tile's main loop.
+// Why TS: with A and B both in shared memory the kernel was bound by the shared-memory port (210 KB per K-block at
+// 128 B/cycle = 1,640 cycles against 830 cycles of tensor work); see DESIGN.md §3.2 and profiles/r01_gemm_trace_notes.txt.
+// Partial tiles rely on TMA's zero fill for out-of-bounds rows / columns; stores are bounds-checked.
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"   // dropout_keep8 / dropout_threshold (the mask definition is shared)
