@@ -143,3 +143,28 @@ def test_gcnconv_oracle_hand_computed():
             [z[2][0] + 0.25, z[2][1] - 0.5],                               # node 2 <- itself
             [0.25, -0.5]]                                                  # node 3: no in-edge
     assert torch.equal(conv(x, ei), torch.tensor(want, dtype=torch.float64))
+
+
+def test_ct_oracle_hand_computed_exchange():
+    """CTLoss restatement (reference src/utils/losses.py:19-49) on a 4-sample, 2-class case worked by hand: each network
+    is trained on the samples its PEER ranks easiest; forget_rate 0.5 keeps int(0.5 * 4) = 2 of them."""
+    import math
+
+    import torch
+    from oracle import ct_oracle
+    # logits chosen so that per-sample CE is log(1 + exp(-m)) with margins m (target class always 0)
+    m1 = [3.0, -1.0, 2.0, 0.0]      # network 1: easiest samples are 0 and 2
+    m2 = [-2.0, 4.0, 1.0, 0.5]      # network 2: easiest samples are 1 and 2
+    y1 = torch.tensor([[m, 0.0] for m in m1], dtype=torch.float64)
+    y2 = torch.tensor([[m, 0.0] for m in m2], dtype=torch.float64)
+    yn = torch.zeros(4, dtype=torch.long)
+    ind = torch.tensor([7, 5, 3, 1, 0])                         # batch.n_id (seeds first)
+    clean = torch.tensor([1, 0, 0, 1, 0, 1, 0, 0], dtype=torch.float64)   # noise_or_not by global id
+    l1, l2, p1, p2, u1, u2, n1, n2 = ct_oracle.ct_loss(y1, y2, yn, 0.5, ind, clean)
+    ce = lambda m: math.log1p(math.exp(-m))
+    assert u1.tolist() == [0, 2] and n1.tolist() == [3, 1]      # ascending loss under network 1: 0, 2, 3, 1
+    assert u2.tolist() == [1, 2] and n2.tolist() == [3, 0]      # under network 2: 1, 2, 3, 0
+    assert abs(float(l1) - (ce(m1[1]) + ce(m1[2])) / 2) < 1e-12   # network 1 on network 2's selection {1, 2}
+    assert abs(float(l2) - (ce(m2[0]) + ce(m2[2])) / 2) < 1e-12   # network 2 on network 1's selection {0, 2}
+    assert float(p1) == float(clean[7] + clean[3]) / 2 == 0.5     # global ids of samples 0 and 2: one clean, one not
+    assert float(p2) == float(clean[5] + clean[3]) / 2 == 1.0     # global ids of samples 1 and 2: both clean
