@@ -153,8 +153,14 @@ def run_ours(args):
 
     K, W = args.steps, args.warmup
     nb = loader.num_batches_global
-    if W + K > len(loader):
-        raise SystemExit(f"--steps + --warmup = {W + K} exceeds one epoch ({len(loader)} steps per rank)")
+
+    def batches(start_epoch=0):
+        """Endless stream of batches: epoch after epoch from `start_epoch` (W + K may exceed one epoch, e.g. 49 steps per
+        rank at 8 GPUs); the same start epoch replays the same blocks."""
+        loader.epoch = start_epoch
+        while True:
+            for b in loader:
+                yield b
 
     def barrier():
         if world > 1:
@@ -180,22 +186,17 @@ def run_ours(args):
     # ---- untimed pre-warm (part of setup): grows the caching allocator's pools, loads every kernel variant, lets the
     #      clocks ramp.  The W warm-up steps the contract asks for still run before each timed region.
     loader.seeds_on_device = True
-    loader.epoch = 0
-    done = 0
-    while done < PREWARM_STEPS:
-        it = iter(loader)
-        for _ in range(min(PREWARM_STEPS - done, len(loader))):
-            step_fn(next(it))
-            done += 1
-        del it
+    it = batches(0)
+    for _ in range(PREWARM_STEPS):
+        step_fn(next(it))
+    it.close()
     H = len(sh.fanouts)
     cap_n, cap_e = loader.max_nodes, loader.max_edges
     torch.cuda.synchronize()
 
     # ---- timed region 1: `value` — every input (graph, features, labels, the epoch's seed order) resident in HBM ----
     loader.seeds_on_device = True
-    loader.epoch = 0
-    it = iter(loader)
+    it = batches(0)
     for _ in range(W):
         step_fn(next(it))
     trainer.reset_stats()
@@ -236,7 +237,7 @@ def run_ours(args):
     clock_info = clocks.stop()
     launches = lib.ngnn_launch_count() - launches0
     ops.timers = None
-    del it
+    it.close()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     edges_total = sum_over_ranks(edges)
     value = edges_total / (ms_total * 1e-3)
@@ -260,8 +261,7 @@ def run_ours(args):
     # algorithmic bytes of each timed layer-1 launch: the sampler is a pure function of (seed, epoch, batch), so the same
     # blocks are sampled again here, outside the timed region, and their distinct table rows counted
     loader.seeds_on_device = True
-    loader.epoch = 0
-    it = iter(loader)
+    it = batches(0)
     for _ in range(W):
         next(it)
     agg_bytes = []
@@ -269,7 +269,7 @@ def run_ours(args):
         blk = next(it).block
         n_dst, e1, _ = SAGE.layer_extents(blk, sh.layers)[0]
         agg_bytes.append(agg_l1_bytes(torch.cat([blk.col_global[:e1], blk.n_id[:n_dst]]), n_dst, e1, sh.features))
-    del it
+    it.close()
     achieved = (sum(agg_bytes) / len(agg_bytes)) / (sum(agg_ms) / len(agg_ms) * 1e-3) / 1e9 if agg_ms else None
     roofline = {"kernel": "k_agg_fwd_pipe<1,6,true> (K-AGG layer 1: mean of sampled in-neighbours + root gather from the resident table)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -285,8 +285,7 @@ def run_ours(args):
 
     # ---- timed region 2: `e2e` — public API with HOST seed buffers; loss / accuracy read back every step ----
     loader.seeds_on_device = False
-    loader.epoch = 0
-    it = iter(loader)
+    it = batches(0)
     for _ in range(W):
         step_fn(next(it))
     barrier()
@@ -309,7 +308,7 @@ def run_ours(args):
     e1_.record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
-    del it
+    it.close()
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1_), wall_ms))
     e2e_value = sum_over_ranks(edges2) / (e2e_ms * 1e-3)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sh.batch_size * 8,
@@ -322,8 +321,7 @@ def run_ours(args):
     # (single process only: the autograd variant all-reduces in its optimizer step, so running it on rank 0 alone
     #  would leave the other ranks' collectives unmatched)
     if not args.no_breakdown and rank == 0 and world == 1:
-        loader.epoch = 0
-        it = iter(loader)
+        it = batches(0)
         for _ in range(W):
             trainer.train_step_autograd(next(it))
         ops.timers, ops.timers_open = {}, True
@@ -334,7 +332,7 @@ def run_ours(args):
         breakdown = {k: round(1e3 * sum(a.elapsed_time(b) for a, b in v) / nbk, 2)
                      for k, v in sorted(ops.timers.items())}          # us per step
         ops.timers, ops.timers_open = None, False
-        del it
+        it.close()
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
     cpu_baseline = None
