@@ -24,6 +24,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 PREWARM_STEPS = int(os.environ.get("NGNN_BENCH_PREWARM", "300"))   # untimed, part of setup (~0.2 s)
+REF_MAX_STEPS, REF_MAX_WARMUP = 40, 2        # --impl reference: ~3 s per CPU step
 METRIC = "sampled_edges_per_sec"
 UNIT = "edges/s"
 
@@ -434,9 +435,14 @@ def run_reference(args):
     loader = NeighborLoader(data, input_nodes=train_idx, num_neighbors=list(sh.fanouts), batch_size=sh.batch_size,
                             shuffle=True, seed=1232)
     order = loader.epoch_permutation(0)
-    K, W = args.steps, args.warmup
+    # One CPU step of this workload takes ~3 s on the box's 16 cores: the run is bounded to a few minutes by timing at most
+    # REF_MAX_STEPS of the requested K steps (and REF_MAX_WARMUP of the W warm-ups); the metric is a rate, `steps` says
+    # how many were timed.
+    K, W = min(args.steps, REF_MAX_STEPS), min(args.warmup, REF_MAX_WARMUP)
     seeds = [loader.batch_seeds(order, i % loader.num_batches_global) for i in range(K + W)]
     res = run_cpu_steps(loader, data, sh, seeds, warmup=W)
+    if (K, W) != (args.steps, args.warmup):
+        res["sample"] += f"; bounded from the requested --steps {args.steps} --warmup {args.warmup}"
     out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K,
            "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
