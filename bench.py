@@ -414,7 +414,14 @@ def run_cpu_steps(loader, data, sh, seed_batches, warmup=1, threads=None):
     dt = time.perf_counter() - t0
     th.join()
     steps = len(seed_batches) - warmup
-    return {"value": edges / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    cpu_model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu_model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), None)
+    except OSError:
+        pass
+    return {"value": edges / dt, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model,
+            "torch_threads": torch.get_num_threads(),
             "sample": f"{steps} train steps (bs {len(seed_batches[0])}, fan-out {fan}, whole sampled block per layer as the "
                       f"reference computes) after {warmup} warm-up, sampler in a prefetch thread (num_workers=1)",
             "ms_per_step": 1e3 * dt / steps, "cpu_count": os.cpu_count()}
