@@ -296,7 +296,8 @@ int32_t ngnn_sage_backward(const ngnn_sage_model_t* model, const float* params, 
  *   stats[0..5] += loss_1, loss_2 (means over the selected rows), #correct_1, #correct_2, pure_ratio_1, pure_ratio_2
  *   dlogits1/2 (optional): gradient of loss_1 / loss_2 w.r.t. logits1 / logits2;   order1/2 (optional, [bs]): row
  *   indices in ascending loss order (order[:num_remember] = the reference's ind_update, the rest = ind_noisy).
- *   scratch: 12*bs floats.  num_remember = int((1 - forget_rate) * bs), computed by the caller like the reference. */
+ *   scratch: 12*bs floats.  num_remember = int((1 - forget_rate) * bs), computed by the caller like the reference;
+ *   num_remember == 0 gives zero losses and gradients (the reference divides by zero there).                       */
 int32_t ngnn_ct_loss(const float* logits1, int64_t ld1, const float* logits2, int64_t ld2, const int64_t* target,
                      const int64_t* y_true, const int32_t* row_ids, const uint8_t* clean_mask, int64_t bs, int64_t C,
                      int64_t num_remember, float* stats /*[6]*/, float* dlogits1, int64_t ldd1, float* dlogits2,
