@@ -71,6 +71,27 @@ class Data:
         return f"Data({', '.join(parts)})"
 
 
+class _DeviceIndex(torch.Tensor):
+    """``Batch.n_id``: an int64 index tensor on the GPU that may also index a HOST tensor.
+
+    The reference's layer-wise inference does ``x_all[batch.n_id].to(device)`` with ``x_all`` on the CPU
+    (src/models/layers/sage.py:50) — with PyG the batch is still on the CPU at that point.  Our batches are born on the
+    device, and torch refuses to index a CPU tensor with a CUDA index; this subclass makes exactly that one expression
+    work (the ids are copied to the host for it — a synchronising D2H, the price of running the reference's loop
+    unmodified; ``noise_gnn_b200.SAGE.inference`` keeps everything on the GPU instead).  Every other operation behaves
+    like, and returns, a plain tensor."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        with torch._C.DisableTorchFunctionSubclass():
+            if (func is torch.Tensor.__getitem__ and len(args) == 2 and isinstance(args[1], cls)
+                    and isinstance(args[0], torch.Tensor) and args[0].device != args[1].device):
+                return args[0][args[1].as_subclass(torch.Tensor).to(args[0].device)]
+            args = tuple(a.as_subclass(torch.Tensor) if isinstance(a, cls) else a for a in args)
+            return func(*args, **kwargs)
+
+
 class Batch:
     """One sampled message-flow block, resident on the device.
 
@@ -114,7 +135,7 @@ class Batch:
             v = ops.csr_to_coo(self.block.rowptr, self.block.col, self.block.n_rows, self.block.e)
             v._ngnn_block = self.block
         elif name == "n_id":
-            v = self._n_id32.long()
+            v = self._n_id32.long().as_subclass(_DeviceIndex)
         elif name == "e_id":
             if self._e_pos is None:
                 raise AttributeError("e_id was not requested (NeighborLoader(..., return_e_id=True))")

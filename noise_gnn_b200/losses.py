@@ -17,19 +17,20 @@ import torch
 from . import ops
 
 
-class _CTLossFunction(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, y_1, y_2, y_noise, num_remember, clean_rows):
-        stats, d1, d2, o1, o2 = ops.ct_loss(y_1.detach(), y_2.detach(), y_noise, num_remember, clean_mask=clean_rows,
-                                            want_grad=True, want_order=True)
-        ctx.save_for_backward(d1, d2)
-        ctx.mark_non_differentiable(o1, o2)
-        return stats[0], stats[1], stats[4], stats[5], o1, o2
+class _ScaledGrad(torch.autograd.Function):
+    """loss value with a precomputed gradient: d(loss)/d(logits) = d.  One node PER loss, each saving only its own
+    gradient, so the reference's pattern ``loss_1.backward(); optimizer1.step(); loss_2.backward()``
+    (src/pipeline.py:127-133) works: the first backward frees nothing the second one needs."""
 
     @staticmethod
-    def backward(ctx, g1, g2, *_):
-        d1, d2 = ctx.saved_tensors
-        return d1 * g1, d2 * g2, None, None, None
+    def forward(ctx, logits, value, d):
+        ctx.save_for_backward(d)
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return d * g, None, None
 
 
 class CTLoss(torch.nn.Module):
@@ -45,7 +46,12 @@ class CTLoss(torch.nn.Module):
         clean_rows = None
         if noise_or_not is not None and ind is not None:               # reference: noise_or_not[ind.cpu()[...]] on the host
             clean_rows = torch.as_tensor(noise_or_not).to(y_1.device).view(-1)[ind[:n].long()].to(torch.uint8)
-        loss_1, loss_2, pure_1, pure_2, o1, o2 = _CTLossFunction.apply(y_1.float(), y_2.float(), y_noise.view(-1),
-                                                                       num_remember, clean_rows)
+        y_1, y_2 = y_1.float(), y_2.float()
+        with torch.no_grad():      # both per-sample losses, the device-side ranking / exchange and both gradients: one call
+            stats, d1, d2, o1, o2 = ops.ct_loss(y_1, y_2, y_noise.view(-1), num_remember, clean_mask=clean_rows,
+                                                want_grad=True, want_order=True)
+        loss_1 = _ScaledGrad.apply(y_1, stats[0], d1)
+        loss_2 = _ScaledGrad.apply(y_2, stats[1], d2)
+        pure_1, pure_2 = stats[4], stats[5]
         o1, o2 = o1.long(), o2.long()
         return (loss_1, loss_2, pure_1, pure_2, o1[:num_remember], o2[:num_remember], o1[num_remember:], o2[num_remember:])

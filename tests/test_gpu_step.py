@@ -263,3 +263,31 @@ def test_hot_rows_first_table_addresses_the_same_rows(dev):
         tr.forward_backward(batch)
         grads.append(tr.buckets.grad.clone()); losses.append(tr.read_stats()[0])
     assert losses[0] == losses[1] and torch.equal(grads[0], grads[1])
+
+
+def test_ctloss_two_backwards_two_optimizers_like_the_reference(dev):
+    """The reference's train_ct (src/pipeline.py:127-133) runs ``loss_1.backward(); optimizer1.step()`` and THEN
+    ``loss_2.backward(); optimizer2.step()`` on the two losses of one CTLoss call: each loss must carry its own autograd
+    node (a shared node would have freed its saved tensors at the first backward)."""
+    from noise_gnn_b200 import CTLoss
+    from oracle import ct_oracle
+    g = torch.Generator().manual_seed(3)
+    bs, C, forget = 200, 7, 0.3
+    w1 = torch.randn(16, C, generator=g).double().requires_grad_(True)
+    w2 = torch.randn(16, C, generator=g).double().requires_grad_(True)
+    x = torch.randn(bs, 16, generator=g).double()
+    yn = torch.randint(0, C, (bs,), generator=g)
+    ind = torch.arange(bs)
+    clean = torch.rand(bs, generator=g) < 0.7
+    want = ct_oracle.ct_loss(x @ w1, x @ w2, yn, forget, ind, clean)
+    want[0].backward(); want[1].backward()
+    a1 = w1.detach().float().to(dev).requires_grad_(True)
+    a2 = w2.detach().float().to(dev).requires_grad_(True)
+    opt1, opt2 = torch.optim.SGD([a1], lr=0.1), torch.optim.SGD([a2], lr=0.1)
+    xd = x.float().to(dev)
+    got = CTLoss(dev)(xd @ a1, xd @ a2, yn.to(dev), forget, ind.to(dev), clean.to(dev))
+    opt1.zero_grad(); got[0].backward(); opt1.step()
+    g1 = a1.grad.clone()
+    opt2.zero_grad(); got[1].backward(); opt2.step()              # second backward through the same CTLoss call
+    assert rel_err(g1, w1.grad) < 1e-5 and rel_err(a2.grad, w2.grad) < 1e-5
+    assert rel_err(got[0].detach(), want[0].detach()) < 1e-5 and rel_err(got[1].detach(), want[1].detach()) < 1e-5

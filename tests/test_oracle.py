@@ -168,3 +168,18 @@ def test_ct_oracle_hand_computed_exchange():
     assert abs(float(l2) - (ce(m2[0]) + ce(m2[2])) / 2) < 1e-12   # network 2 on network 1's selection {0, 2}
     assert float(p1) == float(clean[7] + clean[3]) / 2 == 0.5     # global ids of samples 0 and 2: one clean, one not
     assert float(p2) == float(clean[5] + clean[3]) / 2 == 1.0     # global ids of samples 1 and 2: both clean
+
+
+def test_ctloss_autograd_nodes_are_independent():
+    """CPU check of the autograd plumbing behind the drop-in CTLoss (no kernel call): two losses with precomputed
+    gradients backpropagate one after the other, as the reference's train_ct does (src/pipeline.py:127-133)."""
+    import torch
+    from noise_gnn_b200.losses import _ScaledGrad
+    y1 = torch.randn(5, 3, requires_grad=True)
+    y2 = torch.randn(5, 3, requires_grad=True)
+    d1, d2 = torch.randn(5, 3), torch.randn(5, 3)
+    l1 = _ScaledGrad.apply(y1 * 1.0, torch.tensor(1.5), d1)
+    l2 = _ScaledGrad.apply(y2 * 1.0, torch.tensor(2.5), d2)
+    l1.backward()
+    (l2 * 2).backward()
+    assert torch.equal(y1.grad, d1) and torch.equal(y2.grad, d2 * 2) and float(l1) == 1.5
