@@ -52,6 +52,19 @@ int32_t ngnn_device_supported(void);
  * differences it around the timed region to report gpu_launches.                               */
 uint64_t ngnn_launch_count(void);
 
+/* Per-step control words in DEVICE memory: what changes between two replays of a captured step.  ngnn_step_ctl_set is a
+ * one-thread kernel whose values travel as launch arguments (no host buffer has to outlive the call); the sampler reads
+ * (epoch, batch_idx) from it, the K-GEMM epilogues the dropout stream offset (+ layer index), the loss its weight. */
+typedef struct {
+  uint32_t epoch, batch_idx;
+  uint32_t drop_offset_lo, drop_offset_hi;
+  float    loss_scale;    /* weight of this batch's loss gradient: 1 on one GPU; data parallel: bs_r * R / sum_r bs_r, so that the
+                             all-reduced mean is the GLOBAL-batch mean; 0 masks a padded (wrapped-around) batch out entirely */
+  uint32_t reserved[3];
+} ngnn_step_ctl_t;
+int32_t ngnn_step_ctl_set(ngnn_step_ctl_t* ctl /*device*/, uint32_t epoch, uint32_t batch_idx, uint64_t drop_offset,
+                          float loss_scale, ngnn_stream_t stream);
+
 /* ---- block structure (replaces PyG's COO->CSC conversion) ---- */
 /* Stable sort of a COO edge list by destination:
  *   perm = argsort_stable(dst); col = src[perm]; rowptr[i] = #edges with dst < i.
@@ -98,9 +111,9 @@ int32_t ngnn_gcn_agg_fwd(const int32_t* rowptr, const int32_t* col, const float*
 /* Development knobs for kernel sweeps and A/B measurements (profiles/prof_agg.py, profiles/prof_gemm.py, NGNN_TUNING in
  * bench.py).  key 0: neighbour rows in flight per lane of K-AGG for F <= 128 (0 = default); 1: CTA size of the generic
  * aggregation kernel (128/256/512); 2: lanes per row for 64 < F <= 128 (32/16/8); 3: software-pipelined persistent K-AGG
- * (1 = default); 4: widest N tile of the tcgen05 GEMM (128 = default, 256); 5: shared-memory-staged K-AGG variant
- * (0 = off, 100*(mode+1) + 10*chunk_sel + stages: mode 0 UBLKCP, 1 LDGSTS); 6: A operand of the tcgen05 kernels in
- * tensor memory (1 = default) or shared memory (0); 7: L2 evict_last priority on the layer-1 table gathers (1 = default). */
+ * (1 = default); 4: widest N tile of the tcgen05 GEMM (128 = default, 256); 6: A operand of the tcgen05 kernels in
+ * tensor memory (1 = default) or shared memory (0); 7: L2 evict_last priority on the layer-1 table gathers (1 = default);
+ * 8: number of reduction slices of the tcgen05 K-WGRAD (0 = automatic: one wave of CTAs). */
 int32_t ngnn_set_tuning(int32_t key, int32_t value);
 
 /* ---- K-AGG-T: transpose (CSC) segment sum, backward of K-AGG ----
@@ -212,6 +225,24 @@ int32_t ngnn_sample_block(const int32_t* colptr, const int32_t* row, int64_t N,
                           int32_t* n_id, int32_t* rowptr, int32_t* col, int32_t* col_global, int32_t* e_pos,
                           int32_t* counts, void* ws, size_t ws_bytes, ngnn_stream_t stream);
 
+/* The same, plus what a replayed (CUDA-graph) step needs:
+ *   ctl (device, optional): when non-NULL the RNG key (epoch, batch_idx) is read from it on the device instead of from the
+ *       arguments, so one captured launch sequence samples a different block at every replay;
+ *   num_transposes = T (0..min(H,4)), colptr_t / row_t (host arrays of T device pointers): the CSC transposes of the hop
+ *       prefixes b = 1..T — the first counts[H+1+b] edges over the counts[b] local nodes they touch — which the backward's
+ *       atomic-free transpose segment-sum reads (layer l of L uses b = min(L-l+1, H)).  colptr_t[b-1] has capacity
+ *       (cumulative nodes after hop b-1) + 1, row_t[b-1] capacity (cumulative edges after hop b-1); every row lists its
+ *       destinations in ascending order (= ascending edge position: the stable order of ngnn_csr_transpose).
+ * 5 + 2H kernel launches, none of them a library primitive, no host synchronisation.                              */
+int32_t ngnn_sample_block_ex(const int32_t* colptr, const int32_t* row, int64_t N,
+                             const int64_t* seeds, int32_t bs, const int32_t* fanouts /*(host)[H]*/, int32_t H,
+                             int32_t replace, uint64_t seed, uint32_t epoch, uint32_t batch_idx,
+                             const ngnn_step_ctl_t* ctl /*device, optional*/,
+                             int32_t* n_id, int32_t* rowptr, int32_t* col, int32_t* col_global, int32_t* e_pos,
+                             int32_t* edge_dst /*[e] local destination id per edge; may be NULL when T == 0*/,
+                             int32_t* counts, int32_t num_transposes, int32_t* const* colptr_t /*(host)[T]*/,
+                             int32_t* const* row_t /*(host)[T]*/, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
 /* Table rows of a sampled block for a feature table stored in another row order (remap[global id] = table row, int32 [N]):
  * col_table[p] = remap[col_global[p]] for p < e, n_table[i] = remap[n_id[i]] for i < n, with n / e read from the
  * sampler's device-side `counts` (no host round trip; grids sized by max_nodes / max_edges).                     */
@@ -251,6 +282,16 @@ typedef struct {
   const int32_t* col_table;
   const int32_t* n_table;
   int64_t        hot_rows;
+  /* Device-side extents (optional).  counts = the sampler's device array [2*(H+1)] (ngnn_sample_block): when non-NULL,
+   * hop_nodes / hop_edges may be NULL, the step reads every extent on the device and sizes its launches for the
+   * declared capacities (max_hop_nodes / max_hop_edges), so the launch sequence does not depend on the block and the
+   * step can be captured in a CUDA graph and replayed on the next block written into the same buffers.  Requires
+   * batch_size (host: number of seeds = counts[0]) and, for training, the transposes colptr_t / row_t built by
+   * ngnn_sample_block_ex.  ctl (device, optional): per-replay control words; the dropout stream offset is then
+   * ctl->drop_offset + layer index instead of the drop_offset argument.                                         */
+  const int32_t* counts;
+  int32_t        batch_size;
+  const ngnn_step_ctl_t* ctl;
 } ngnn_block_t;
 
 int64_t ngnn_sage_num_params(const ngnn_sage_model_t* model);

@@ -47,6 +47,9 @@ SIGNATURES = {
     "ngnn_sage_step_workspace_bytes": (c_size_t, [_P, c_int32, _P, _P]),
     "ngnn_sage_step": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, c_uint64, c_uint64, _P, _P, c_int64, _P,
                                  c_size_t, _P]),
+    "ngnn_sample_block_ex": (c_int32, [_P, _P, c_int64, _P, c_int32, _P, c_int32, c_int32, c_uint64, c_uint32, c_uint32, _P,
+                                       _P, _P, _P, _P, _P, _P, _P, c_int32, _P, _P, _P, c_size_t, _P]),
+    "ngnn_step_ctl_set": (c_int32, [_P, c_uint32, c_uint32, c_uint64, c_float, _P]),
     "ngnn_block_table_index": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, _P, _P, _P]),
     "ngnn_sage_forward": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_uint64, c_uint64, _P, c_int64, _P, c_size_t, _P]),
     "ngnn_sage_backward": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_size_t, _P]),
@@ -75,7 +78,8 @@ class BlockDesc(ctypes.Structure):      # ngnn_block_t
     _fields_ = [("rowptr", c_void_p), ("col", c_void_p), ("col_global", c_void_p), ("n_id", c_void_p),
                 ("num_hops", c_int32), ("hop_nodes", ctypes.POINTER(c_int32)), ("hop_edges", ctypes.POINTER(c_int32)),
                 ("colptr_t", c_void_p * 8), ("row_t", c_void_p * 8),
-                ("col_table", c_void_p), ("n_table", c_void_p), ("hot_rows", c_int64)]
+                ("col_table", c_void_p), ("n_table", c_void_p), ("hot_rows", c_int64),
+                ("counts", c_void_p), ("batch_size", c_int32), ("ctl", c_void_p)]
 
 
 _lib = None

@@ -19,7 +19,8 @@ struct AggParams {
   const int32_t* idx;      // col (fwd) / row_t (bwd), [e]
   const float* x;          // source rows
   int64_t ld_x;
-  int64_t n_rows;
+  int64_t n_rows;          // number of output rows (the launch bound / capacity when n_rows_dev != nullptr)
+  const int32_t* n_rows_dev;  // optional device-side row count (a sampled block's extent), clamped to n_rows
   int64_t F;
   float* out;
   int64_t ld_out;
@@ -27,6 +28,7 @@ struct AggParams {
   const float* add;        // optional rows added for i < n_add (bwd: dx_root)
   int64_t ld_add;
   int64_t n_add;
+  const int32_t* n_add_dev; // optional device-side n_add (clamped to n_add)
   const float* act_ref;    // optional gate: out *= (act_ref > 0 ? act_scale : 0)
   int64_t ld_act;
   float act_scale;
@@ -40,9 +42,16 @@ struct AggParams {
 
 __device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
-}  // namespace ngnn
-#include "agg_bulk.cuh"   // k_agg_fwd_bulk: rows staged through shared memory by the async copy engines
-namespace ngnn {
+__device__ __forceinline__ int64_t agg_n_add(const AggParams& p) {
+  if (p.n_add_dev == nullptr) return p.n_add;
+  const int64_t v = (int64_t)__ldg(p.n_add_dev);
+  return v < p.n_add ? (v < 0 ? 0 : v) : p.n_add;
+}
+__device__ __forceinline__ int64_t agg_rows(const AggParams& p) {
+  if (p.n_rows_dev == nullptr) return p.n_rows;
+  const int64_t v = (int64_t)__ldg(p.n_rows_dev);
+  return v < p.n_rows ? (v < 0 ? 0 : v) : p.n_rows;
+}
 
 // Gather-accumulate of the neighbours [beg, end) of one output row into acc (columns c0 + gl + v*G), U rows in flight.
 template <int G, int VPL, int U>
@@ -121,29 +130,30 @@ __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gw * G));
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t row = warp * GROUPS_PER_WARP + gw;
-  const bool valid = row < p.n_rows;
+  const int64_t n_rows = agg_rows(p);
+  const bool valid = row < n_rows;
   if (!COOP && !valid) return;
   if (COOP) {
     if (threadIdx.x == 0) s_nlong = 0;
     __syncthreads();
   }
 
-  const int F4 = (int)(p.F >> 2);
+  const int F4 = (int)((p.F + 3) >> 2);             // a partial last vector reads / writes the rows' padding (ld >= 4*F4)
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   int beg = 0, end = 0;
   if (valid) {
     // The extents and the indices are two small arrays read strictly in row order: each group asks L2 for the sectors
     // the rows kPrefetchRows further on will need.
     constexpr int64_t kPrefetchRows = 16384;
-    const int e_total = __ldg(p.ptr + p.n_rows);
-    if (gl == 0 && row + kPrefetchRows <= p.n_rows) prefetch_l2(p.ptr + row + kPrefetchRows);
+    const int e_total = __ldg(p.ptr + n_rows);
+    if (gl == 0 && row + kPrefetchRows <= n_rows) prefetch_l2(p.ptr + row + kPrefetchRows);
     beg = __ldg(p.ptr + row); end = __ldg(p.ptr + row + 1);
     if (gl == 0 && (int64_t)beg + kPrefetchRows < e_total) prefetch_l2(p.idx + beg + kPrefetchRows);
   }
   const bool is_long = COOP && valid && (end - beg) > kLongRow;
   if (valid && !is_long) {
     const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
-    const bool has_add = p.add != nullptr && row < p.n_add;
+    const bool has_add = p.add != nullptr && row < agg_n_add(p);
     for (int c0 = 0; c0 < F4; c0 += G * VPL) {
       float4 acc[VPL];
 #pragma unroll
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
       const int slice = ((lend - lbeg + nw - 1) / nw + 31) & ~31;          // whole 32-index windows per warp
       const int sb = min(lend, lbeg + wib * slice), se = wib < nw ? min(lend, sb + slice) : sb;
       const float scale = p.mean ? 1.0f / (float)max(lend - lbeg, 1) : 1.0f;
-      const bool has_add = p.add != nullptr && lrow < p.n_add;
+      const bool has_add = p.add != nullptr && lrow < agg_n_add(p);
       for (int c0 = 0; c0 < F4; c0 += 32 * VPL) {
         float4 acc[VPL];
 #pragma unroll
@@ -209,7 +219,7 @@ template <int VPL>
 __global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (row >= p.n_rows) return;
+  if (row >= agg_rows(p)) return;
   const int F = (int)p.F;
   const int beg = __ldg(p.ptr + row), end = __ldg(p.ptr + row + 1);
   const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
       if (c >= F) continue;
       float r = acc[v] * scale;
       if (p.bias != nullptr) r += __ldg(p.bias + c);
-      if (p.add != nullptr && row < p.n_add) r += __ldg(p.add + row * p.ld_add + c);
+      if (p.add != nullptr && row < agg_n_add(p)) r += __ldg(p.add + row * p.ld_add + c);
       if (p.act_ref != nullptr) r = __ldg(p.act_ref + row * p.ld_act + c) > 0.f ? r * p.act_scale : 0.f;
       p.out[row * p.ld_out + c] = r;
     }
@@ -267,8 +277,8 @@ template <int VPL, int U, bool ROOT>
 __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n = p.n_rows;
-  const int F4 = (int)(p.F >> 2);
+  const int64_t n = agg_rows(p);
+  const int F4 = (int)((p.F + 3) >> 2);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // ROOT = gathering from the resident feature table (layer 1): keep its rows in L2 ahead of the streaming activations
@@ -359,44 +369,6 @@ static int g_tune_threads = 256; // ngnn_set_tuning(1, t): CTA size 128 / 256 / 
 static int g_tune_pipe = 1;      // ngnn_set_tuning(3, 0/1): software-pipelined persistent forward kernel
 static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 < F <= 128 (32 / 16 / 8)
 static int g_tune_keep = 1;      // ngnn_set_tuning(7, 0|1): L2 evict_last priority on the layer-1 table gathers
-static int g_tune_bulk = 0;      // ngnn_set_tuning(5, v): 0 = off, else 100*mode + 10*chunk_sel + stage_sel (see launch_bulk)
-
-template <int CH, int S, int MODE, bool ROOT>
-static bool launch_bulk_one(const AggParams& p, cudaStream_t st) {
-  const size_t smem = agg_bulk_smem_bytes(CH, S, p.F);
-  if (smem > 227 * 1024) return false;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(k_agg_fwd_bulk<CH, S, MODE, ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    configured = true;
-  }
-  int64_t grid = kNumSMs;                                            // persistent: one CTA per SM
-  const int64_t need = ceil_div(p.n_rows, kBulkWarps);
-  if (grid > need) grid = need;
-  k_agg_fwd_bulk<CH, S, MODE, ROOT><<<(unsigned)grid, kBulkWarps * 32, smem, st>>>(p);
-  return true;
-}
-
-// v = 100*(mode+1) + 10*chunk_sel + stages: chunk_sel 0 -> 8 neighbours per unit, 1 -> 16; stages in {3,4,6}
-template <bool ROOT>
-static bool launch_bulk(const AggParams& p, cudaStream_t st, int v) {
-  const int mode = v / 100 - 1, ch = (v / 10) % 10, s = v % 10;
-  if (mode == 0) {
-    if (ch == 0 && s == 4) return launch_bulk_one<8, 4, 0, ROOT>(p, st);
-    if (ch == 0 && s == 6) return launch_bulk_one<8, 6, 0, ROOT>(p, st);
-    if (ch == 1 && s == 3) return launch_bulk_one<16, 3, 0, ROOT>(p, st);
-    if (ch == 1 && s == 4) return launch_bulk_one<16, 4, 0, ROOT>(p, st);
-  } else if (mode == 1) {
-    if (ch == 0 && s == 4) return launch_bulk_one<8, 4, 1, ROOT>(p, st);
-    if (ch == 0 && s == 6) return launch_bulk_one<8, 6, 1, ROOT>(p, st);
-    if (ch == 1 && s == 3) return launch_bulk_one<16, 3, 1, ROOT>(p, st);
-    if (ch == 1 && s == 4) return launch_bulk_one<16, 4, 1, ROOT>(p, st);
-  }
-  return false;
-}
 
 template <int G, int VPL, int U>
 static void launch_v4(const AggParams& p, cudaStream_t st) {
@@ -407,18 +379,18 @@ static void launch_v4(const AggParams& p, cudaStream_t st) {
 
 static int32_t run_agg(const AggParams& p, cudaStream_t st) {
   if (p.n_rows == 0 || p.F == 0) return NGNN_OK;
-  bool vec = (p.F % 4 == 0) && (p.ld_x % 4 == 0) && (p.ld_out % 4 == 0) && is_aligned(p.x, 16) && is_aligned(p.out, 16);
-  if (p.add) vec = vec && (p.ld_add % 4 == 0) && is_aligned(p.add, 16);
-  if (p.act_ref) vec = vec && (p.ld_act % 4 == 0) && is_aligned(p.act_ref, 16);
-  if (p.root_idx) vec = vec && (p.ld_root % 4 == 0) && is_aligned(p.root, 16);
-  if (p.bias) vec = vec && is_aligned(p.bias, 16);
+  // 128-bit path: rows addressed as whole float4 vectors.  A width that is not a multiple of 4 (1433, 767) qualifies when
+  // every row has the padding behind it (ld >= 4*ceil(F/4), as the loader's table and the step arena guarantee): the last
+  // vector then reads / writes pad columns, which no consumer looks at.
+  const int64_t F4 = (p.F + 3) / 4, Fv = 4 * F4;
+  auto rows_ok = [&](const void* base, int64_t ld) { return (ld % 4 == 0) && ld >= Fv && is_aligned(base, 16); };
+  bool vec = rows_ok(p.x, p.ld_x) && rows_ok(p.out, p.ld_out);
+  if (p.add) vec = vec && rows_ok(p.add, p.ld_add);
+  if (p.act_ref) vec = vec && rows_ok(p.act_ref, p.ld_act);
+  if (p.root_idx) vec = vec && rows_ok(p.root, p.ld_root);
+  if (p.bias) vec = vec && is_aligned(p.bias, 16) && p.F % 4 == 0;
   if (vec) {
-    const int64_t F4 = p.F / 4;
     const bool fwd_plain = p.add == nullptr && p.act_ref == nullptr && p.bias == nullptr;   // forward aggregation (mean [+ root gather])
-    if (fwd_plain && g_tune_bulk && F4 <= 32 && p.n_rows < (1ll << 31)) {
-      const bool ok = p.root_idx ? launch_bulk<true>(p, st, g_tune_bulk) : launch_bulk<false>(p, st, g_tune_bulk);
-      if (ok) { NGNN_LAUNCH_CHECK(); return NGNN_OK; }
-    }
     if (fwd_plain && g_tune_pipe && F4 > 16 && F4 <= 64) {
       if (F4 <= 32) {
         const int u = g_tune_unroll;
@@ -460,18 +432,45 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
 }  // namespace ngnn
 
 namespace ngnn {
-int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, int64_t n_dst,
+int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, Ext n_dst,
                            int64_t F, float* mean, int64_t ld_mean, const int32_t* root_table, float* root, int64_t ld_root,
                            int64_t hot_rows, cudaStream_t st) {
-  if (n_dst == 0 || F == 0) return NGNN_OK;
+  if (n_dst.cap == 0 || F == 0) return NGNN_OK;
   NGNN_REQUIRE(rowptr && table && mean && ld_table >= F && ld_mean >= F, NGNN_E_INVALID, "agg_fwd_table: bad arguments");
   // (Measured, round 1: reserving an L2 persisting set-aside for the hot rows — cudaLimitPersistingL2CacheSize — made this
   //  kernel slower, 57 us vs 52 us with the plain cache hints, so no device-wide limit is touched.)
   AggParams p{};
-  p.ptr = rowptr; p.idx = col_table; p.x = table; p.ld_x = ld_table; p.n_rows = n_dst; p.F = F;
+  p.ptr = rowptr; p.idx = col_table; p.x = table; p.ld_x = ld_table; p.n_rows = n_dst.cap; p.n_rows_dev = n_dst.dev; p.F = F;
   p.out = mean; p.ld_out = ld_mean; p.mean = 1;
   p.root_idx = root_table; p.root = root; p.ld_root = ld_root;
   p.keep_l2 = g_tune_keep; p.hot_rows = hot_rows;
+  return run_agg(p, st);
+}
+
+int32_t agg_fwd_impl(const int32_t* rowptr, const int32_t* col, const float* x, int64_t ld_x, Ext n_dst, int64_t F, float* mean,
+                     int64_t ld_mean, cudaStream_t st) {
+  if (n_dst.cap == 0 || F == 0) return NGNN_OK;
+  NGNN_REQUIRE(rowptr && x && mean && ld_x >= F && ld_mean >= F, NGNN_E_INVALID, "agg_fwd: bad arguments");
+  AggParams p{};
+  p.ptr = rowptr; p.idx = col; p.x = x; p.ld_x = ld_x; p.n_rows = n_dst.cap; p.n_rows_dev = n_dst.dev; p.F = F;
+  p.out = mean; p.ld_out = ld_mean; p.mean = 1;
+  p.keep_l2 = g_tune_keep; p.hot_rows = -1;
+  return run_agg(p, st);
+}
+
+int32_t agg_bwd_impl(const int32_t* colptr_t, const int32_t* row_t, const float* dmean_scaled, int64_t ld_dmean, Ext n_src,
+                     int64_t F, const float* dx_root, int64_t ld_root, Ext n_root, const float* act_ref, int64_t ld_act,
+                     float act_scale, float* dx, int64_t ld_dx, cudaStream_t st) {
+  if (n_src.cap == 0 || F == 0) return NGNN_OK;
+  NGNN_REQUIRE(colptr_t && dmean_scaled && dx, NGNN_E_INVALID, "agg_bwd: null pointer");
+  NGNN_REQUIRE(ld_dmean >= F && ld_dx >= F, NGNN_E_INVALID, "agg_bwd: leading dimension < F");
+  NGNN_REQUIRE(dx_root == nullptr || ld_root >= F, NGNN_E_INVALID, "agg_bwd: ld_root < F");
+  NGNN_REQUIRE(act_ref == nullptr || ld_act >= F, NGNN_E_INVALID, "agg_bwd: ld_act < F");
+  AggParams p{};
+  p.ptr = colptr_t; p.idx = row_t; p.x = dmean_scaled; p.ld_x = ld_dmean; p.n_rows = n_src.cap; p.n_rows_dev = n_src.dev; p.F = F;
+  p.out = dx; p.ld_out = ld_dx; p.mean = 0;
+  p.add = dx_root; p.ld_add = ld_root; p.n_add = dx_root ? n_root.cap : 0; p.n_add_dev = dx_root ? n_root.dev : nullptr;
+  p.act_ref = act_ref; p.ld_act = ld_act; p.act_scale = act_scale;
   return run_agg(p, st);
 }
 }  // namespace ngnn
@@ -480,6 +479,7 @@ using namespace ngnn;
 
 extern "C" int32_t ngnn_set_gemm_tile(int32_t bn_max);   // gemm.cu
 extern "C" int32_t ngnn_set_gemm_ts(int32_t on);         // gemm.cu
+extern "C" int32_t ngnn_set_wgrad_splits(int32_t s);     // gemm.cu
 
 extern "C" {
 
@@ -489,7 +489,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 2 && (value == 32 || value == 16 || value == 8)) { g_tune_group = value; return NGNN_OK; }
   if (key == 3 && (value == 0 || value == 1)) { g_tune_pipe = value; return NGNN_OK; }
   if (key == 4 && (value == 128 || value == 256)) return ngnn_set_gemm_tile(value);
-  if (key == 5 && value >= 0 && value < 300) { g_tune_bulk = value; return NGNN_OK; }
+  if (key == 8 && value >= 0 && value <= 4096) return ngnn_set_wgrad_splits(value);
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);
@@ -529,16 +529,8 @@ int32_t ngnn_sage_agg_bwd(const int32_t* colptr_t, const int32_t* row_t, const f
                           ngnn_stream_t stream) {
   NGNN_REQUIRE(n_src >= 0 && F >= 0 && n_root >= 0, NGNN_E_INVALID, "agg_bwd: negative size");
   if (n_src == 0 || F == 0) return NGNN_OK;
-  NGNN_REQUIRE(colptr_t && dmean_scaled && dx, NGNN_E_INVALID, "agg_bwd: null pointer");
-  NGNN_REQUIRE(ld_dmean >= F && ld_dx >= F, NGNN_E_INVALID, "agg_bwd: leading dimension < F");
-  NGNN_REQUIRE(dx_root == nullptr || ld_root >= F, NGNN_E_INVALID, "agg_bwd: ld_root < F");
-  NGNN_REQUIRE(act_ref == nullptr || ld_act >= F, NGNN_E_INVALID, "agg_bwd: ld_act < F");
-  AggParams p{};
-  p.ptr = colptr_t; p.idx = row_t; p.x = dmean_scaled; p.ld_x = ld_dmean; p.n_rows = n_src; p.F = F;
-  p.out = dx; p.ld_out = ld_dx; p.mean = 0;
-  p.add = dx_root; p.ld_add = ld_root; p.n_add = dx_root ? n_root : 0;
-  p.act_ref = act_ref; p.ld_act = ld_act; p.act_scale = act_scale;
-  return run_agg(p, as_stream(stream));
+  return agg_bwd_impl(colptr_t, row_t, dmean_scaled, ld_dmean, ext_host(n_src), F, dx_root, ld_root, ext_host(n_root), act_ref,
+                      ld_act, act_scale, dx, ld_dx, as_stream(stream));
 }
 
 }  // extern "C"

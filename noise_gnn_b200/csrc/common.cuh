@@ -45,6 +45,32 @@ static inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cas
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
+// An extent (row / edge count) that may live in device memory.  A sampled block's sizes are only known on the device
+// (the sampler writes them to `counts`); kernels launched with worst-case grids read them there, so a whole step is a
+// FIXED launch sequence with no host round trip and can be captured in a CUDA graph.  `cap` is the host-side bound: the
+// exact value when dev == nullptr, the capacity of the buffers otherwise (the device value is clamped to it).
+struct Ext {
+  const int32_t* dev;
+  int64_t cap;
+};
+static inline Ext ext_host(int64_t n) { return Ext{nullptr, n}; }
+static inline Ext ext_dev(const int32_t* p, int64_t cap) { return Ext{p, cap}; }
+__device__ __forceinline__ int64_t ext_get(const Ext& e) {
+  if (e.dev == nullptr) return e.cap;
+  const int64_t v = (int64_t)__ldg(e.dev);
+  return v < e.cap ? (v < 0 ? 0 : v) : e.cap;
+}
+
+// Per-step control words in device memory (ngnn_step_ctl_t): what changes from one replay of a captured step to the
+// next.  Written by ngnn_step_ctl_set (a one-thread kernel whose arguments travel by value, so no host buffer has to
+// outlive the launch) and read by the sampler (RNG key) and the K-GEMM epilogues (dropout stream offset).
+struct StepCtl {
+  uint32_t epoch, batch_idx;
+  uint32_t drop_off_lo, drop_off_hi;
+  uint32_t loss_scale_bits;      // float: weight of this batch's loss gradient (data parallel: bs_r * R / sum bs; 0 = padded batch)
+  uint32_t reserved[3];
+};
+
 // Library-internal entry points of the dense kernels (gemm.cu) for the fused step (step.cu): the split weight planes
 // are prepared once per step, off the critical path, instead of inside every GEMM call.
 //   mode 0: forward pack [W_l | W_r] (K-major) -> ws of ngnn_sage_gemm_workspace_bytes(F, O)
@@ -52,9 +78,14 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 // Returns NGNN_E_UNSUPPORTED when the shape takes the SIMT kernels (which read the weights directly).
 // K-AGG forward from the resident feature table with a hot-row split (agg.cu): table rows < hot_rows are gathered with
 // L2 evict_last priority, the rest with evict_first (hot_rows < 0: every row evict_last).
-int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, int64_t n_dst,
+int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, Ext n_dst,
                            int64_t F, float* mean, int64_t ld_mean, const int32_t* root_table, float* root, int64_t ld_root,
                            int64_t hot_rows, cudaStream_t st);
+int32_t agg_fwd_impl(const int32_t* rowptr, const int32_t* col, const float* x, int64_t ld_x, Ext n_dst, int64_t F, float* mean,
+                     int64_t ld_mean, cudaStream_t st);
+int32_t agg_bwd_impl(const int32_t* colptr_t, const int32_t* row_t, const float* dmean_scaled, int64_t ld_dmean, Ext n_src,
+                     int64_t F, const float* dx_root, int64_t ld_root, Ext n_root, const float* act_ref, int64_t ld_act,
+                     float act_scale, float* dx, int64_t ld_dx, cudaStream_t st);
 int32_t prep_weights_impl(int32_t mode, const float* w_l, const float* w_r, int64_t F, int64_t O, void* ws, size_t ws_bytes,
                           cudaStream_t st);
 // Batched form: prep_batch_add collects jobs (same arguments / return codes), prep_batch_launch runs them in one launch.
@@ -64,10 +95,16 @@ int32_t prep_batch_launch(cudaStream_t st);
 int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l, const float* w_r,
                       const float* bias, int64_t n, int64_t F, int64_t O, int32_t act, float drop_p, uint64_t seed,
                       uint64_t offset, float* out, int64_t ld_out, int32_t* path, void* ws, size_t ws_bytes, cudaStream_t st,
-                      bool prepped);
+                      bool prepped, const int32_t* n_dev, const struct StepCtl* ctl, uint32_t ctl_layer);
 int32_t dgrad_impl(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr, int64_t n,
                    int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root, int64_t ld_root, void* ws,
-                   size_t ws_bytes, cudaStream_t st, bool prepped);
+                   size_t ws_bytes, cudaStream_t st, bool prepped, const int32_t* n_dev);
+int32_t ce_impl(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true, const int32_t* row_ids,
+                int64_t bs, int64_t C, float grad_scale, float* stats, float* dlogits, int64_t ld_d, float* row_scratch,
+                const struct StepCtl* ctl, cudaStream_t st);
+int32_t wgrad_impl(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, int64_t n,
+                   const int32_t* n_dev, int64_t F, int64_t O, float* dw_l, float* dw_r, float* db, int32_t accumulate,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: the same (key, counter)

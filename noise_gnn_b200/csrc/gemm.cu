@@ -70,7 +70,7 @@ int32_t prep_batch_launch(cudaStream_t st) {
 int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l, const float* w_r,
                       const float* bias, int64_t n, int64_t F, int64_t O, int32_t act, float drop_p, uint64_t seed,
                       uint64_t offset, float* out, int64_t ld_out, int32_t* path, void* ws, size_t ws_bytes, cudaStream_t st,
-                      bool prepped) {
+                      bool prepped, const int32_t* n_dev, const StepCtl* ctl, uint32_t ctl_layer) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "gemm_fwd: negative size");
   NGNN_REQUIRE(act == NGNN_ACT_NONE || act == NGNN_ACT_RELU, NGNN_E_INVALID, "gemm_fwd: unknown activation %d", act);
   NGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, NGNN_E_INVALID, "gemm_fwd: dropout p=%f outside [0,1)", (double)drop_p);
@@ -84,10 +84,12 @@ int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t
 
   if (!g_force_simt) {
     int32_t rc = tc_gemm_fwd(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out,
-                             ws, ws_bytes, st, prepped);
+                             ws, ws_bytes, st, prepped, n_dev, ctl, ctl_layer);
     if (rc == NGNN_OK) { if (path) *path = 1; return NGNN_OK; }
     if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
+  NGNN_REQUIRE(n_dev == nullptr && ctl == nullptr, NGNN_E_UNSUPPORTED,
+               "gemm_fwd: device-side extents need TMA-addressable operands (16-byte aligned bases, ld %% 4 == 0)");
 
   SimtGemmParams p{};
   if (a_l) { p.A1 = {a_l, ld_al, 1}; p.B1 = {w_l, F, 1}; p.K1 = F; }
@@ -100,7 +102,7 @@ int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t
 
 int32_t dgrad_impl(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr, int64_t n,
                    int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root, int64_t ld_root, void* ws,
-                   size_t ws_bytes, cudaStream_t st, bool prepped) {
+                   size_t ws_bytes, cudaStream_t st, bool prepped, const int32_t* n_dev) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "dgrad: negative size");
   if (n == 0 || F == 0) return NGNN_OK;
   NGNN_REQUIRE(dy && ld_dy >= O, NGNN_E_INVALID, "dgrad: bad dy");
@@ -109,9 +111,10 @@ int32_t dgrad_impl(const float* dy, int64_t ld_dy, const float* w_l, const float
   // out[i,f] = sum_o dy[i,o] * W[o,f]  : A = dy (K = O contiguous), B(n=f,k=o) = W[o*F + f]
   if (!g_force_simt) {
     int32_t rc = tc_gemm_dgrad(dy, ld_dy, w_l, w_r, rowptr, n, F, O, dmean_scaled, ld_dmean, dx_root, ld_root, ws,
-                               ws_bytes, st, prepped);
+                               ws_bytes, st, prepped, n_dev);
     if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
+  NGNN_REQUIRE(n_dev == nullptr, NGNN_E_UNSUPPORTED, "dgrad: device-side extents need TMA-addressable operands");
   if (dmean_scaled) {
     SimtGemmParams p{};
     p.A1 = {dy, ld_dy, 1}; p.B1 = {w_l, 1, F}; p.K1 = O;
@@ -129,59 +132,14 @@ int32_t dgrad_impl(const float* dy, int64_t ld_dy, const float* w_l, const float
   return NGNN_OK;
 }
 
-}  // namespace ngnn
-
-using namespace ngnn;
-
-extern "C" {
-
-int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
-                           const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
-                           float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, int32_t* path,
-                           void* ws, size_t ws_bytes, ngnn_stream_t stream) {
-  return gemm_fwd_impl(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out, path, ws,
-                       ws_bytes, as_stream(stream), false);
-}
-
-int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
-                        int64_t n, int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root,
-                        int64_t ld_root, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
-  return dgrad_impl(dy, ld_dy, w_l, w_r, rowptr, n, F, O, dmean_scaled, ld_dmean, dx_root, ld_root, ws, ws_bytes,
-                    as_stream(stream), false);
-}
-
-int32_t ngnn_set_gemm_tile(int32_t bn_max) { g_tc_bn_max = bn_max; return NGNN_OK; }   // reached through ngnn_set_tuning(4, .)
-int32_t ngnn_set_gemm_ts(int32_t on) { g_tc_ts = on; return NGNN_OK; }                  // reached through ngnn_set_tuning(6, .)
-
-int32_t ngnn_debug_set_trace(void* device_buffer) {
-  g_tc_trace = reinterpret_cast<long long*>(device_buffer);
-  return NGNN_OK;
-}
-
-int32_t ngnn_set_gemm_path(int32_t mode) {
-  NGNN_REQUIRE(mode == 0 || mode == 1, NGNN_E_INVALID, "set_gemm_path: mode must be 0 (auto) or 1 (force SIMT)");
-  g_force_simt = mode;
-  return NGNN_OK;
-}
-
-size_t ngnn_sage_gemm_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_fwd_ws_bytes(F, O) : 256; }
-size_t ngnn_sage_dgrad_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_dgrad_ws_bytes(F, O) : 256; }
-
 static size_t colsum_ws_bytes(int64_t n, int64_t O) { return align_up((size_t)colsum_slices(n, O) * (size_t)O * sizeof(float), 256); }
 
-size_t ngnn_sage_wgrad_workspace_bytes(int64_t n, int64_t F, int64_t O) {
-  if (n <= 0 || F < 0 || O <= 0) return 256;
-  const size_t simt = align_up((size_t)wgrad_splits(n, F, O) * (size_t)O * (size_t)F * sizeof(float), 256);
-  const size_t tc = F >= 4 ? tc_wgrad_ws_bytes(n, F, O) : 0;
-  return colsum_ws_bytes(n, O) + (simt > tc ? simt : tc) + 512;
-}
-
-int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r,
-                        int64_t ld_ar, int64_t n, int64_t F, int64_t O, float* dw_l, float* dw_r, float* db,
-                        int32_t accumulate, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+// n_dev (optional): device-side number of rows; n is then the capacity every launch is sized for.
+int32_t wgrad_impl(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, int64_t n,
+                   const int32_t* n_dev, int64_t F, int64_t O, float* dw_l, float* dw_r, float* db, int32_t accumulate,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "wgrad: negative size");
   if (O == 0) return NGNN_OK;
-  cudaStream_t st = as_stream(stream);
   if (n == 0) {  // empty block: gradients are zero
     if (!accumulate) {
       if (dw_l && F) NGNN_CUDA(cudaMemsetAsync(dw_l, 0, (size_t)O * F * sizeof(float), st));
@@ -202,11 +160,12 @@ int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_
   // dW[o,f] = sum_i dy[i,o] * a[i,f] : A(m=o,k=i) = dy[i*ld+o], B(n=f,k=i) = a[i*ld+f]
   bool done = false;
   if (!g_force_simt && F > 0 && (dw_l || dw_r)) {
-    int32_t rc = tc_gemm_wgrad(dy, ld_dy, a_l, ld_al, a_r, ld_ar, n, F, O, dw_l, dw_r, accumulate, part, part_bytes, st);
+    int32_t rc = tc_gemm_wgrad(dy, ld_dy, a_l, ld_al, a_r, ld_ar, n, n_dev, F, O, dw_l, dw_r, accumulate, part, part_bytes, st);
     if (rc == NGNN_OK) done = true;
     else if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
-  if (!done) {
+  if (!done && (dw_l || dw_r)) {
+    NGNN_REQUIRE(n_dev == nullptr, NGNN_E_UNSUPPORTED, "wgrad: device-side extents need TMA-addressable operands");
     const int32_t S = wgrad_splits(n, F, O);
     const float* as[2] = {a_l, a_r};
     const int64_t lds[2] = {ld_al, ld_ar};
@@ -231,14 +190,66 @@ int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_
   }
   if (db) {
     const int32_t Cs = colsum_slices(n, O);
-    const int64_t rows = ceil_div(n, Cs);
     dim3 grid((unsigned)ceil_div(O, 32), (unsigned)Cs);
-    k_colsum_partial<<<grid, 256, 0, st>>>(dy, ld_dy, n, O, rows, cpart);
+    k_colsum_partial<<<grid, 256, 0, st>>>(dy, ld_dy, Ext{n_dev, n}, O, cpart);
     NGNN_LAUNCH_CHECK();
     k_reduce_partials<<<(unsigned)ceil_div(O, 256), 256, 0, st>>>(cpart, O, Cs, O, db, accumulate);
     NGNN_LAUNCH_CHECK();
   }
   return NGNN_OK;
+}
+
+}  // namespace ngnn
+
+using namespace ngnn;
+
+extern "C" {
+
+int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
+                           const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
+                           float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, int32_t* path,
+                           void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  return gemm_fwd_impl(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out, path, ws,
+                       ws_bytes, as_stream(stream), false, nullptr, nullptr, 0);
+}
+
+int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
+                        int64_t n, int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root,
+                        int64_t ld_root, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  return dgrad_impl(dy, ld_dy, w_l, w_r, rowptr, n, F, O, dmean_scaled, ld_dmean, dx_root, ld_root, ws, ws_bytes,
+                    as_stream(stream), false, nullptr);
+}
+
+int32_t ngnn_set_gemm_tile(int32_t bn_max) { g_tc_bn_max = bn_max; return NGNN_OK; }   // reached through ngnn_set_tuning(4, .)
+int32_t ngnn_set_gemm_ts(int32_t on) { g_tc_ts = on; return NGNN_OK; }                  // reached through ngnn_set_tuning(6, .)
+int32_t ngnn_set_wgrad_splits(int32_t s) { g_tc_wgrad_splits = s; return NGNN_OK; }     // reached through ngnn_set_tuning(8, .)
+
+int32_t ngnn_debug_set_trace(void* device_buffer) {
+  g_tc_trace = reinterpret_cast<long long*>(device_buffer);
+  return NGNN_OK;
+}
+
+int32_t ngnn_set_gemm_path(int32_t mode) {
+  NGNN_REQUIRE(mode == 0 || mode == 1, NGNN_E_INVALID, "set_gemm_path: mode must be 0 (auto) or 1 (force SIMT)");
+  g_force_simt = mode;
+  return NGNN_OK;
+}
+
+size_t ngnn_sage_gemm_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_fwd_ws_bytes(F, O) : 256; }
+size_t ngnn_sage_dgrad_workspace_bytes(int64_t F, int64_t O) { return (F > 0 && O > 0) ? tc_dgrad_ws_bytes(F, O) : 256; }
+
+size_t ngnn_sage_wgrad_workspace_bytes(int64_t n, int64_t F, int64_t O) {
+  if (n <= 0 || F < 0 || O <= 0) return 256;
+  const size_t simt = align_up((size_t)wgrad_splits(n, F, O) * (size_t)O * (size_t)F * sizeof(float), 256);
+  const size_t tc = F >= 1 ? tc_wgrad_ws_bytes(n, F, O) : 0;
+  return colsum_ws_bytes(n, O) + (simt > tc ? simt : tc) + 512;
+}
+
+int32_t ngnn_sage_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r,
+                        int64_t ld_ar, int64_t n, int64_t F, int64_t O, float* dw_l, float* dw_r, float* db,
+                        int32_t accumulate, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  return wgrad_impl(dy, ld_dy, a_l, ld_al, a_r, ld_ar, n, nullptr, F, O, dw_l, dw_r, db, accumulate, ws, ws_bytes,
+                    as_stream(stream));
 }
 
 int32_t ngnn_act_bwd(const float* dh, int64_t ld_dh, const float* h, int64_t ld_h, int64_t n, int64_t O, float scale,

@@ -209,12 +209,14 @@ __global__ void k_reduce_partials2(const float* __restrict__ part0, const float*
 // column sums of dy over a row slice: part[z*O + o] = sum_{i in slice z} dy[i*ld + o].
 // Block = 32 columns x 8 row lanes: every warp reads 128 contiguous bytes of a row; the 8 row lanes are combined
 // through shared memory in a fixed order (deterministic).
-__global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict__ dy, int64_t ld, int64_t n, int64_t O,
-                                                        int64_t rows_per_slice, float* __restrict__ part) {
+__global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict__ dy, int64_t ld, Ext n_ext, int64_t O,
+                                                        float* __restrict__ part) {
   __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t o = (int64_t)blockIdx.x * 32 + tx;
-  const int64_t i0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t n = ext_get(n_ext);
+  const int64_t rows_per_slice = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t i0 = min(n, (int64_t)blockIdx.y * rows_per_slice);
   const int64_t i1 = min(n, i0 + rows_per_slice);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (o < O) {

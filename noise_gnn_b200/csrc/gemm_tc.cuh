@@ -302,7 +302,10 @@ struct TcSegment {            // one N range of the packed B matrix and where it
   int32_t scale_rows;         // 1: scale row m by 1/max(rowptr[m+1]-rowptr[m],1)
 };
 struct TcGemmParams {
-  int32_t M;                  // rows
+  int32_t M;                  // rows (capacity when M_dev != nullptr)
+  const int32_t* M_dev;       // optional device-side row count (clamped to M): the tensor maps and the grid are sized for M
+  const StepCtl* ctl;         // optional device-side step control: dropout offset = ctl->drop_off + ctl_layer
+  uint32_t ctl_layer;
   int32_t BN;                 // UMMA N / columns per CTA tile
   int32_t kblocks1, kblocks2; // K-blocks of operand pair 1 / 2
   int32_t b_koff2;            // k offset (floats) of pair 2 in the packed B planes
@@ -363,7 +366,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t KB = p.kblocks1 + p.kblocks2;
-  const int32_t m_tiles = (p.M + TC_BM - 1) / TC_BM;
+  int32_t M = p.M;
+  if (p.M_dev != nullptr) { const int32_t v = __ldg(p.M_dev); M = v < p.M ? (v < 0 ? 0 : v) : p.M; }
+  const int32_t m_tiles = (M + TC_BM - 1) / TC_BM;
   const int32_t total_tiles = m_tiles * p.tiles_per_seg * p.num_segs;
   uint32_t buf_cols = 32;
   while (buf_cols < (uint32_t)p.BN) buf_cols <<= 1;
@@ -524,6 +529,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
     float* stage = epi_stage + (warp - 6) * EPI16_PATCH;
     const uint32_t thr = dropout_threshold(p.drop_p);
     const float keep_scale = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    uint32_t off_lo = p.off_lo, off_hi = p.off_hi;
+    if (p.ctl != nullptr) {                          // replayed step: the dropout stream offset lives on the device
+      const uint64_t o = (((uint64_t)p.ctl->drop_off_hi << 32) | p.ctl->drop_off_lo) + p.ctl_layer;
+      off_lo = (uint32_t)o; off_hi = (uint32_t)(o >> 32);
+    }
     // last chunk this warp reads from TMEM (-1: none — it hands the buffer back right away)
     int32_t last_c = -1;
     for (int32_t c = 32 * half; c < p.BN; c += 64) last_c = c;
@@ -539,7 +549,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
       epi_bar_sync();
       const int64_t row0 = (int64_t)m0 + q * 32;
       const int64_t m = row0 + lane;
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < M;
       float rs = 1.0f;
       if (sg.scale_rows && p.rowptr != nullptr && row_ok)
         rs = 1.0f / (float)max(__ldg(p.rowptr + m + 1) - __ldg(p.rowptr + m), 1);
@@ -566,9 +576,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
           if (!live) continue;
           uint32_t keep16 = 0xFFFFu;                              // nb is a multiple of 16: two 8-column Philox groups
           if (p.drop_p > 0.f && row_ok) {
-            keep16 = dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3), p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr);
+            keep16 = dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3), p.seed_lo, p.seed_hi, off_lo, off_hi, thr);
             if (nb + 8 < sg.n_cols)
-              keep16 |= dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3) + 1u, p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr) << 8;
+              keep16 |= dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3) + 1u, p.seed_lo, p.seed_hi, off_lo, off_hi, thr) << 8;
           }
           float r[16];
 #pragma unroll
@@ -583,7 +593,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
               r[4 * g + jj] = x;
             }
           }
-          epilogue_store16(stage, r, sg.out, sg.ld_out, row0, p.M, nb, sg.n_cols, vec_ok, lane);
+          epilogue_store16(stage, r, sg.out, sg.ld_out, row0, M, nb, sg.n_cols, vec_ok, lane);
         }
       }
       if (tr && et == 0 && j == 0) tr[3] = clock64();
@@ -692,9 +702,13 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
 // operands are not TMA-addressable; the caller then uses the SIMT kernel.
 // Packed hi / lo weight planes of the forward projection ([W_l | W_r], K-major) into ws.  `use_l` / `use_r`: which operand
 // pairs the GEMM will contract (a missing one is zero-filled).
+// A tensor-memory accumulation chain longer than this many K-blocks (x 12 MMAs, each rounding the accumulator toward zero)
+// drifts past the 1e-5 bar (see the K-WGRAD notes below): wider contractions take the SIMT kernel.
+constexpr int TC_MAX_CHAIN_KBLOCKS = 40;
+
 static inline int32_t tc_prep_fwd(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
                                   size_t ws_bytes, cudaStream_t st, PrepParams* collect = nullptr) {
-  if (F % 4 != 0 || F < 4 || O < 1) return NGNN_E_UNSUPPORTED;
+  if (F < 1 || O < 1 || 2 * ceil_div(F, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_fwd_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
   const int32_t Fpad = round_up_i(F, TC_BK), Kpack = 2 * Fpad;
   float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
@@ -712,8 +726,10 @@ static inline int32_t tc_prep_fwd(const float* w_l, const float* w_r, bool use_l
 static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l,
                                   const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
                                   float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, void* ws,
-                                  size_t ws_bytes, cudaStream_t st, bool prepped = false) {
-  if (F % 4 != 0 || F < 4 || n < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+                                  size_t ws_bytes, cudaStream_t st, bool prepped = false, const int32_t* n_dev = nullptr,
+                                  const StepCtl* ctl = nullptr, uint32_t ctl_layer = 0) {
+  if (F < 1 || n < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+  if (2 * ceil_div(F, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
   if (a_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
   if (a_r && !tma_addressable(a_r, ld_ar)) return NGNN_E_UNSUPPORTED;
   if (!a_l && !a_r) return NGNN_E_UNSUPPORTED;
@@ -739,7 +755,8 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
   NGNN_REQUIRE(ok, NGNN_E_CUDA, "gemm_fwd: cuTensorMapEncodeTiled failed");
 
   TcGemmParams p{};
-  p.M = (int32_t)n; p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
+  p.M = (int32_t)n; p.M_dev = n_dev; p.ctl = ctl; p.ctl_layer = ctl_layer;
+  p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
   p.kblocks1 = Fpad / TC_BK; p.kblocks2 = two ? Fpad / TC_BK : 0;
   p.b_koff2 = Fpad;
   if (!a_l) { p.b_koff2 = 0; /* single operand is a_r: its weights sit in segment 1 of the pack */ }
@@ -762,7 +779,7 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
 // Packed hi / lo planes of [W_l^T ; W_r^T] (rows = F per segment, K = O) for the data gradient.
 static inline int32_t tc_prep_dgrad(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
                                     size_t ws_bytes, cudaStream_t st, PrepParams* collect = nullptr) {
-  if (F < 1 || O < 1) return NGNN_E_UNSUPPORTED;
+  if (F < 1 || O < 1 || ceil_div(O, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_dgrad_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
   const int32_t Kpack = round_up_i(O, TC_BK), Rpad = round_up_i(F, 16);
   const int32_t rows = 2 * Rpad;
@@ -780,8 +797,10 @@ static inline int32_t tc_prep_dgrad(const float* w_l, const float* w_r, bool use
 
 static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,
                                     int64_t n, int64_t F, int64_t O, float* dmean, int64_t ld_dmean, float* droot,
-                                    int64_t ld_root, void* ws, size_t ws_bytes, cudaStream_t st, bool prepped = false) {
+                                    int64_t ld_root, void* ws, size_t ws_bytes, cudaStream_t st, bool prepped = false,
+                                    const int32_t* n_dev = nullptr) {
   if (n < 1 || F < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+  if (ceil_div(O, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
   if (!tma_addressable(dy, ld_dy)) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_dgrad_ws_bytes(F, O) || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
   if (!dmean && !droot) return NGNN_OK;
@@ -803,7 +822,7 @@ static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float*
   NGNN_REQUIRE(ok, NGNN_E_CUDA, "dgrad: cuTensorMapEncodeTiled failed");
 
   TcGemmParams p{};
-  p.M = (int32_t)n; p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
+  p.M = (int32_t)n; p.M_dev = n_dev; p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
   p.kblocks1 = Kpack / TC_BK; p.kblocks2 = 0; p.b_koff2 = 0;
   p.rowptr = rowptr;
   int ns = 0;
@@ -818,10 +837,23 @@ static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float*
 // For 32-bit MN-major operands the only UMMA shared-memory layout is SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 128
 // bytes (32 MN elements) with the 32-byte chunks of a row XOR-ed by (row % 4) — what TMA writes for a
 // [32 rows(i) x 32 floats] box with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The 32-wide MN groups of a tile are
-// LBO = 4096 B (one box) apart, the 4-row k groups SBO = 512 B apart.  The long i dimension is split across CTAs (grid.z) into fixed
+// LBO = 4096 B (one box) apart, the 4-row k groups SBO = 512 B apart.  The long i dimension is split across CTAs (grid.z) into
 // slices; each CTA writes its partial tile and k_reduce_partials sums them in a fixed order (deterministic).
+//
+// Accumulation accuracy.  The tensor core adds into its fp32 accumulator with round-toward-zero, so a long chain of MMAs
+// drifts by up to one ulp PER MMA, always toward zero — a bias that grows linearly with the chain.  A weight gradient
+// reduces over ~77 k rows (products layer 1: 2,400 K-blocks, 66 per slice, 12 MMAs each) and its terms largely cancel:
+// measured on the full-scale products step, the 800-MMA chains of the first version put dW_l 8e-4 (relative) away from the
+// fp64 oracle, where the fp32 CPU oracle is 8e-7 away.  So the chain is cut: the MMA warp accumulates TW_CHUNK K-blocks
+// (96 MMAs) into one of two TMEM accumulator buffers, then eight "promoter" warps tcgen05.ld that chunk and add it to
+// fp32 running sums held in registers (round-to-nearest FADD on the CUDA cores) while the next chunk's MMAs run into
+// the other buffer.  The chunking depends only on (n, grid), so results stay bitwise reproducible.
 constexpr int TW_KB = 32;                      // reduction rows per K-block
 constexpr uint32_t TW_BOX_BYTES = TW_KB * 128; // one [32 x 32 floats] box
+constexpr int TW_CHUNK = 8;                    // K-blocks (256 reduction rows) per tensor-memory accumulation chain
+constexpr int TW_EPI_WARPS = 8;                // promoter / epilogue warps: two per TMEM lane quarter
+constexpr int TW_THREADS = 192 + 32 * TW_EPI_WARPS;
+constexpr int TW_BN_MAX = 128;                 // 2 accumulator buffers x 128 + 4 x 64 A columns = 512 TMEM columns
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -841,20 +873,22 @@ struct TcWgradSeg {
 };
 struct TcWgradParams {
   int32_t O;                  // rows of dW
-  int32_t BN;                 // UMMA N (multiple of 16)
+  int32_t BN;                 // UMMA N (multiple of 16, <= TW_BN_MAX)
   int32_t nbox;               // ceil(BN / 32) boxes of X per K-block
   int32_t stages;
   int32_t tiles_per_seg;
-  int32_t kblocks_per_split;  // K-blocks (of 32 reduction rows) per grid.z slice
-  int32_t kblocks_total;
+  int32_t n;                  // reduction rows (capacity when n_dev != nullptr)
+  const int32_t* n_dev;       // optional device-side reduction length (clamped to n)
   TcWgradSeg seg[2];
 };
 
 // TS = true: dY^T (the M x K operand) is transposed + split by the converter warps straight into tensor memory
 // (lane = output row o, column = reduction row i), X stays in shared memory (MN-major, split in place): the SS form
 // moved 218 KB per K-block through the 128 B/cycle shared-memory port for 711 cycles of tensor work.
+// Rows >= n of the last K-block are zeroed by the converters in both operands (the tensor maps may cover the buffers'
+// capacity, so TMA's out-of-bounds zero fill cannot be relied on when n lives on the device).
 template <bool TS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TW_THREADS, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX1,
            const __grid_constant__ CUtensorMap tmX2, const TcWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -868,8 +902,9 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* full_conv = full_raw + TC_MAX_STAGES;
   uint64_t* empty = full_conv + TC_MAX_STAGES;
-  uint64_t* tmem_full = empty + TC_MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* acc_full = empty + TC_MAX_STAGES;       // [2]
+  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t o0 = blockIdx.x * TC_BM;
@@ -877,17 +912,23 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
   const int32_t n_tile = blockIdx.y - seg_id * p.tiles_per_seg;
   const TcWgradSeg sg = p.seg[seg_id];
   const int32_t f0 = n_tile * p.BN;
-  const int32_t kb_beg = blockIdx.z * p.kblocks_per_split;
-  const int32_t kb_end = min(p.kblocks_total, kb_beg + p.kblocks_per_split);
-  const int32_t KB = max(kb_end - kb_beg, 0);
-  uint32_t acc_cols = 32;
-  while (acc_cols < (uint32_t)p.BN) acc_cols <<= 1;
-  const uint32_t tmem_cols = TS ? 512u : acc_cols;             // TS: accumulator (<= 256) + 4 x 64 A columns
+  int32_t n = p.n;
+  if (p.n_dev != nullptr) { const int32_t v = __ldg(p.n_dev); n = v < p.n ? (v < 0 ? 0 : v) : p.n; }
+  const int32_t kb_total = (n + TW_KB - 1) / TW_KB;
+  const int32_t kps = (kb_total + (int32_t)gridDim.z - 1) / (int32_t)gridDim.z;      // K-blocks per slice
+  const int32_t kb_beg = min(kb_total, (int32_t)blockIdx.z * kps);
+  const int32_t kb_end = min(kb_total, kb_beg + kps);
+  const int32_t KB = kb_end - kb_beg;
+  const int32_t n_chunks = (KB + TW_CHUNK - 1) / TW_CHUNK;
+  uint32_t buf_cols = 32;
+  while (buf_cols < (uint32_t)p.BN) buf_cols <<= 1;
+  const uint32_t tmem_cols = TS ? 512u : 2 * buf_cols;         // TS: two accumulator buffers (<= 2 x 128) + 4 x 64 A columns
+  const uint32_t tmem_a0 = 2 * buf_cols;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmX2);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 128); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 32 * TW_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -916,54 +957,63 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
     // whole warp in convergence, elect-issued MMAs (warp-uniform operands: see umma_tf32_elect)
     const uint32_t idesc = umma_idesc_tf32(TC_BM, (uint32_t)p.BN, TS ? 0 : 1, 1);   // SS: both operands MN-major; TS: A K-major in TMEM
     StageIter si{0, 0u, p.stages};
-    for (int32_t it = 0; it < KB; ++it, si.next()) {
-      const int s = si.s;
-      mbar_wait(&full_conv[s], si.ph);
+    for (int32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t ab = (uint32_t)c & 1u;
+      mbar_wait(&acc_empty[ab], (((uint32_t)c >> 1) & 1u) ^ 1u);    // the promoters have drained this accumulator buffer
       tc_fence_after();
-      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-      const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + a_span, b_lo = b_hi + b_bytes;
-      const uint32_t ta = tmem_base + acc_cols + (uint32_t)s * TS_A_COLS;
+      const uint32_t tmem_d = tmem_base + ab * buf_cols;
+      const int32_t kbc = min(TW_CHUNK, KB - c * TW_CHUNK);
+      for (int32_t kk = 0; kk < kbc; ++kk, si.next()) {
+        const int s = si.s;
+        mbar_wait(&full_conv[s], si.ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + a_span, b_lo = b_hi + b_bytes;
+        const uint32_t ta = tmem_base + tmem_a0 + (uint32_t)s * TS_A_COLS;
 #pragma unroll
-      for (int k = 0; k < TW_KB / 8; ++k) {
-        const uint32_t koff = k * 1024;   // 8 reduction rows x 128 B
-        const uint64_t dbh = umma_desc_mn_sw128(b_hi + koff, TW_BOX_BYTES, 512), dbl = umma_desc_mn_sw128(b_lo + koff, TW_BOX_BYTES, 512);
-        if (TS) {
-          umma_tf32_ts_elect(tmem_base, ta + k * 8, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_tf32_ts_elect(tmem_base, ta + 32 + k * 8, dbh, idesc, 1u);
-          umma_tf32_ts_elect(tmem_base, ta + k * 8, dbl, idesc, 1u);
-        } else {
-          const uint64_t dah = umma_desc_mn_sw128(a_hi + koff, TW_BOX_BYTES, 512), dal = umma_desc_mn_sw128(a_lo + koff, TW_BOX_BYTES, 512);
-          umma_tf32_elect(tmem_base, dah, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_tf32_elect(tmem_base, dal, dbh, idesc, 1u);
-          umma_tf32_elect(tmem_base, dah, dbl, idesc, 1u);
+        for (int k = 0; k < TW_KB / 8; ++k) {
+          const uint32_t koff = k * 1024;   // 8 reduction rows x 128 B
+          const uint64_t dbh = umma_desc_mn_sw128(b_hi + koff, TW_BOX_BYTES, 512), dbl = umma_desc_mn_sw128(b_lo + koff, TW_BOX_BYTES, 512);
+          if (TS) {
+            umma_tf32_ts_elect(tmem_d, ta + k * 8, dbh, idesc, (kk > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_ts_elect(tmem_d, ta + 32 + k * 8, dbh, idesc, 1u);
+            umma_tf32_ts_elect(tmem_d, ta + k * 8, dbl, idesc, 1u);
+          } else {
+            const uint64_t dah = umma_desc_mn_sw128(a_hi + koff, TW_BOX_BYTES, 512), dal = umma_desc_mn_sw128(a_lo + koff, TW_BOX_BYTES, 512);
+            umma_tf32_elect(tmem_d, dah, dbh, idesc, (kk > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_elect(tmem_d, dal, dbh, idesc, 1u);
+            umma_tf32_elect(tmem_d, dah, dbl, idesc, 1u);
+          }
         }
+        umma_commit_elect(&empty[s]);
+        if (kk == kbc - 1) umma_commit_elect(&acc_full[ab]);       // this chunk's chain is complete
       }
-      umma_commit_elect(&empty[s]);
-      if (it == KB - 1) umma_commit_elect(tmem_full);
     }
-  } else {
+  } else if (warp < 6) {
+    // ===================== converter warps (2..5): hi / lo split of both operands, rows >= n zeroed =====================
     const int t = threadIdx.x - 64;
-    const int n4 = (int)((a_bytes + b_bytes) / 16);            // float4s to split per stage (A then B, hi planes)
     StageIter si{0, 0u, p.stages};
     for (int32_t it = 0; it < KB; ++it, si.next()) {
       const int s = si.s;
       const uint32_t ph = si.ph;
       mbar_wait(&full_raw[s], ph);
       uint8_t* st = smem + (size_t)s * stage_bytes;
+      const int32_t rows_ok = n - (kb_beg + it) * TW_KB;       // reduction rows of this K-block that exist (>= 32: all)
       if (TS) {
         // A: thread = output row o = 32*(warp%4) + lane = column `lane` of box (warp%4); reduction row i of that box is one
         // 128-byte line whose 32-byte chunks are XOR-ed with (i % 4) (SWIZZLE_128B_ATOM_32B) -> a warp reads one full
         // line per i, conflict-free.  32 values -> hi / lo -> 64 TMEM columns of this thread's lane.
         const int qa = warp & 3;
         const float* box = reinterpret_cast<const float*>(st + (size_t)qa * TW_BOX_BYTES);
-        const uint32_t ta = tmem_base + ((uint32_t)(qa * 32) << 16) + acc_cols + (uint32_t)s * TS_A_COLS;
+        const uint32_t ta = tmem_base + ((uint32_t)(qa * 32) << 16) + tmem_a0 + (uint32_t)s * TS_A_COLS;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t h[16], l[16];
 #pragma unroll
           for (int ii = 0; ii < 16; ++ii) {
             const int i = half * 16 + ii;
-            const float x = box[i * 32 + ((((lane >> 3) ^ (i & 3)) << 3) | (lane & 7))];
+            float x = box[i * 32 + ((((lane >> 3) ^ (i & 3)) << 3) | (lane & 7))];
+            if (i >= rows_ok) x = 0.f;
             float hx, lx;
             split_tf32(x, hx, lx);
             h[ii] = __float_as_uint(hx); l[ii] = __float_as_uint(lx);
@@ -971,12 +1021,13 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
           tmem_st16(ta + half * 16, h);
           tmem_st16(ta + 32 + half * 16, l);
         }
-        // B: split in place (hi) + lo plane
+        // B: split in place (hi) + lo plane; float4 q of a box belongs to reduction row (q % 256) / 8
         float4* bh = reinterpret_cast<float4*>(st + a_span);
         float4* bl = reinterpret_cast<float4*>(st + a_span + b_bytes);
         const int b4 = (int)(b_bytes / 16);
         for (int i = t; i < b4; i += 128) {
-          const float4 x = bh[i];
+          float4 x = bh[i];
+          if (((i & 255) >> 3) >= rows_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
           float4 h, l;
           split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
           bh[i] = h;
@@ -985,12 +1036,14 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
         tmem_st_wait();
         tc_fence_before();
       } else {
-        const int a4 = (int)(a_bytes / 16);
+        const int a4 = (int)(a_bytes / 16), n4 = (int)((a_bytes + b_bytes) / 16);
         for (int i = t; i < n4; i += 128) {
           float4* hp; float4* lp;
-          if (i < a4) { hp = reinterpret_cast<float4*>(st) + i; lp = reinterpret_cast<float4*>(st + a_bytes) + i; }
-          else { hp = reinterpret_cast<float4*>(st + 2 * a_bytes) + (i - a4); lp = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes) + (i - a4); }
-          const float4 x = *hp;
+          int q;
+          if (i < a4) { q = i; hp = reinterpret_cast<float4*>(st) + i; lp = reinterpret_cast<float4*>(st + a_bytes) + i; }
+          else { q = i - a4; hp = reinterpret_cast<float4*>(st + 2 * a_bytes) + q; lp = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes) + q; }
+          float4 x = *hp;
+          if (((q & 255) >> 3) >= rows_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
           float4 h, l;
           split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
           *hp = h;
@@ -1000,31 +1053,46 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
       fence_proxy_async_smem();
       mbar_arrive(&full_conv[s]);
     }
-    // epilogue: partial tile -> global (coalesced through a shared-memory staging patch)
+  } else {
+    // ===================== promoter / epilogue warps (6..13) =====================
+    // Two warps per TMEM lane quarter; the pair alternates the tile's 16-column units.  Running sums of up to 4 units
+    // (64 columns) per thread in registers; every finished chain is added in with round-to-nearest.
     const int q = warp & 3;
+    const int half = (warp - 6) >> 2;
+    float sum[4][16];
+#pragma unroll
+    for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) sum[uu][jj] = 0.f;
+    for (int32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t ab = (uint32_t)c & 1u;
+      mbar_wait(&acc_full[ab], ((uint32_t)c >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + ab * buf_cols + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int32_t cc = 16 * (2 * uu + half);
+        if (cc < p.BN) {                                           // warp-uniform
+          uint32_t v[16];
+          tmem_ld16(tmem_d + (uint32_t)cc, v);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) sum[uu][jj] += __uint_as_float(v[jj]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+    }
+    // partial tile -> global, coalesced through a shared-memory staging patch (the ring is idle by now: every K-block of
+    // this CTA has been consumed by MMAs that completed before the last acc_full)
     const int64_t row0 = (int64_t)o0 + q * 32;
     float* obase = sg.out + (int64_t)blockIdx.z * sg.split_stride;
     const bool vec_ok = ((sg.n_cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
-    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * EPI_PATCH;
-    if (KB > 0) {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-    }
-    for (int32_t c = 0; c < p.BN; c += 32) {
-      if (f0 + c >= sg.n_cols) break;
-      uint32_t v[32];
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 6) * EPI16_PATCH;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
-      if (KB > 0) {
-        uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
-        uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v0);
-        if (c + 16 < p.BN) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c + 16), v1);
-      }
-      float r[32];
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) r[jj] = __uint_as_float(v[jj]);
-      epilogue_store32(stage, r, obase, sg.n_cols, row0, p.O, f0 + c, sg.n_cols, vec_ok, lane);
+    for (int uu = 0; uu < 4; ++uu) {
+      const int32_t cc = 16 * (2 * uu + half);
+      if (cc < p.BN && f0 + cc < sg.n_cols)
+        epilogue_store16(stage, sum[uu], obase, sg.n_cols, row0, p.O, f0 + cc, sg.n_cols, vec_ok, lane);
     }
   }
   tc_fence_before();
@@ -1033,13 +1101,14 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
 }
 
 struct TcWgradPlan {
-  int32_t BN, nbox, tiles_per_seg, stages, splits, kblocks_total, kblocks_per_split;
+  int32_t BN, nbox, tiles_per_seg, stages, splits;
   uint32_t smem_bytes;
   bool ts;
 };
+static int g_tc_wgrad_splits = 0;   // ngnn_set_tuning(8, s): force the number of reduction slices (0 = automatic)
 static inline TcWgradPlan tc_wgrad_plan(int64_t n, int64_t F, int64_t O, int num_segs) {
   TcWgradPlan pl;
-  pl.BN = F >= 256 ? 256 : round_up_i(F, 16);
+  pl.BN = F >= TW_BN_MAX ? TW_BN_MAX : round_up_i(F, 16);
   pl.nbox = (pl.BN + 31) / 32;
   pl.tiles_per_seg = (int32_t)ceil_div(F, pl.BN);
   pl.ts = g_tc_ts != 0;
@@ -1047,27 +1116,32 @@ static inline TcWgradPlan tc_wgrad_plan(int64_t n, int64_t F, int64_t O, int num
   int st = (int)((TC_SMEM_LIMIT - 2048u) / stage);
   pl.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
   pl.smem_bytes = (uint32_t)pl.stages * stage + 1024u + 256u;
-  pl.kblocks_total = (int32_t)ceil_div(n, TW_KB);
+  const uint32_t epi = (uint32_t)TW_EPI_WARPS * EPI16_PATCH * 4u + 1024u + 256u;   // the epilogue's staging reuses the ring
+  if (pl.smem_bytes < epi) pl.smem_bytes = epi;
+  const int64_t kblocks = ceil_div(n, TW_KB);
   const int64_t tiles = ceil_div(O, TC_BM) * pl.tiles_per_seg * num_segs;
   int64_t s = kNumSMs / tiles;                                   // one wave of CTAs (1 CTA / SM: smem-bound)
-  const int64_t max_s = ceil_div(pl.kblocks_total, 4);           // at least 4 K-blocks per slice
+  const int64_t max_s = ceil_div(kblocks, 4);                    // at least 4 K-blocks per slice
   if (s > max_s) s = max_s;
+  if (g_tc_wgrad_splits > 0) s = g_tc_wgrad_splits;
   if (s < 1) s = 1;
-  pl.kblocks_per_split = (int32_t)ceil_div(pl.kblocks_total, s);
-  pl.splits = (int32_t)ceil_div(pl.kblocks_total, pl.kblocks_per_split);
+  pl.splits = (int32_t)s;
   return pl;
 }
 // partial planes for both segments
 static inline size_t tc_wgrad_ws_bytes(int64_t n, int64_t F, int64_t O) {
   const TcWgradPlan pl = tc_wgrad_plan(n, F, O, 2);
-  return 2 * align_up((size_t)pl.splits * O * F * sizeof(float), 256) + 256;
+  const TcWgradPlan pl1 = tc_wgrad_plan(n, F, O, 1);
+  const int64_t s = pl.splits > pl1.splits ? pl.splits : pl1.splits;
+  return 2 * align_up((size_t)s * O * F * sizeof(float), 256) + 256;
 }
 
 // dw_l (+)= dy^T a_l ; dw_r (+)= dy^T a_r.  UNSUPPORTED when an operand is not TMA-addressable.
+// n_dev (optional): device-side reduction length, n is then the capacity the launch is sized for.
 static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r,
-                                    int64_t ld_ar, int64_t n, int64_t F, int64_t O, float* dw_l, float* dw_r,
-                                    int32_t accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (n < 1 || F < 4 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+                                    int64_t ld_ar, int64_t n, const int32_t* n_dev, int64_t F, int64_t O, float* dw_l,
+                                    float* dw_r, int32_t accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n < 1 || F < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
   if (!tma_addressable(dy, ld_dy)) return NGNN_E_UNSUPPORTED;
   if (dw_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
   if (dw_r && !tma_addressable(a_r, ld_ar)) return NGNN_E_UNSUPPORTED;
@@ -1090,7 +1164,7 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
   const bool direct = pl.splits == 1 && !accumulate;
   TcWgradParams p{};
   p.O = (int32_t)O; p.BN = pl.BN; p.nbox = pl.nbox; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
-  p.kblocks_per_split = pl.kblocks_per_split; p.kblocks_total = pl.kblocks_total;
+  p.n = (int32_t)n; p.n_dev = n_dev;
   int ns = 0;
   float* outs[2] = {nullptr, nullptr};
   float* parts[2] = {nullptr, nullptr};
@@ -1104,8 +1178,8 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(O, TC_BM), (unsigned)(pl.tiles_per_seg * ns), (unsigned)pl.splits);
-  if (pl.ts) k_tc_wgrad<true><<<grid, TC_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
-  else k_tc_wgrad<false><<<grid, TC_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
+  if (pl.ts) k_tc_wgrad<true><<<grid, TW_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
+  else k_tc_wgrad<false><<<grid, TW_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
   NGNN_LAUNCH_CHECK();
   if (!direct) {
     // same per-element summation order as k_reduce_partials; both weight gradients in one launch

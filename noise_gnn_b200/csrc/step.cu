@@ -18,7 +18,9 @@ namespace ngnn {
 struct LayerPlan {
   int64_t F, O;                 // in / out channels
   int64_t ldo;                  // leading dimension of this layer's out / dy buffers (O rounded up to 4: TMA-addressable)
-  int64_t n_dst, e_lim, n_src;  // trimmed extents of this step
+  int64_t ldf;                  // leading dimension of this layer's mean / root / dmean buffers (F rounded up to 4)
+  int a, b;                     // hop indices of this layer's extents: n_dst = nodes[a], e_lim = edges[b], n_src = nodes[b]
+  int64_t n_dst, e_lim, n_src;  // trimmed extents of this step (host mode; = the capacities in device mode)
   int64_t n_dst_max, e_max, n_src_max;
   size_t off_wl, off_b, off_wr; // element offsets into the flat parameter / gradient buckets
   // arena regions (byte offsets)
@@ -48,8 +50,10 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     lp.F = i == 0 ? m->in_dim : m->hidden_dim;
     lp.O = i == L - 1 ? m->out_dim : m->hidden_dim;
     lp.ldo = (lp.O + 3) / 4 * 4;
+    lp.ldf = (lp.F + 3) / 4 * 4;
     const int d = L - 1 - i;   // hops between this layer's outputs and the seeds
     const int a = d < H ? d : H, b = d + 1 < H ? d + 1 : H;
+    lp.a = a; lp.b = b;
     lp.n_dst_max = max_hop_nodes[a]; lp.e_max = max_hop_edges[b]; lp.n_src_max = max_hop_nodes[b];
     if (hop_nodes) { lp.n_dst = hop_nodes[a]; lp.e_lim = hop_edges[b]; lp.n_src = hop_nodes[b]; }
     else { lp.n_dst = lp.n_dst_max; lp.e_lim = lp.e_max; lp.n_src = lp.n_src_max; }
@@ -57,15 +61,15 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     lp.off_wl = poff; poff += (size_t)lp.O * lp.F;
     lp.off_b = poff; poff += (size_t)lp.O;
     lp.off_wr = poff; poff += (size_t)lp.O * lp.F;
-    lp.mean = take((size_t)lp.n_dst_max * lp.F * 4);
-    lp.root = i == 0 ? take((size_t)lp.n_dst_max * lp.F * 4) : 0;
+    lp.mean = take((size_t)lp.n_dst_max * lp.ldf * 4);
+    lp.root = i == 0 ? take((size_t)lp.n_dst_max * lp.ldf * 4) : 0;
     lp.out = take((size_t)lp.n_dst_max * lp.ldo * 4);
     lp.dy = take((size_t)lp.n_dst_max * lp.ldo * 4);
     if (i > 0) {
       lp.colptr_t = take((size_t)(lp.n_src_max + 1) * 4);
       lp.row_t = take((size_t)lp.e_max * 4);
       lp.perm_t = take((size_t)lp.e_max * 4);
-      if ((size_t)lp.n_dst_max * lp.F * 4 > max_dx) max_dx = (size_t)lp.n_dst_max * lp.F * 4;
+      if ((size_t)lp.n_dst_max * lp.ldf * 4 > max_dx) max_dx = (size_t)lp.n_dst_max * lp.ldf * 4;
       const size_t s = ngnn_csr_transpose_workspace_bytes(lp.e_max, lp.n_src_max);
       if (s > sws) sws = s;
       const size_t dg = ngnn_sage_dgrad_workspace_bytes(lp.F, lp.O);
@@ -91,16 +95,22 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
 // The weight gradients of layers >= 2 are off the backward's critical path (dY_l -> dgrad -> transpose-sum -> dY_{l-1}):
 // they are forked onto an auxiliary stream (event fork / join, graph-capturable) so their small grids run under the
 // dgrad / K-AGG-T chain instead of after it.
-static cudaStream_t g_aux = nullptr;
-static cudaEvent_t g_fork = nullptr, g_join = nullptr, g_prep = nullptr;
+// One set per device (a process may step models on several GPUs); one stepping thread per device at a time.
+struct AuxCtx { cudaStream_t stream; cudaEvent_t fork, join; };
+static AuxCtx g_auxs[64] = {};
 static bool g_use_aux = true;
 
-static int32_t ensure_aux() {
-  if (g_aux != nullptr) return NGNN_OK;
-  NGNN_CUDA(cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking));
-  NGNN_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-  NGNN_CUDA(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
-  NGNN_CUDA(cudaEventCreateWithFlags(&g_prep, cudaEventDisableTiming));
+static int32_t ensure_aux(AuxCtx** out) {
+  int dev = 0;
+  NGNN_CUDA(cudaGetDevice(&dev));
+  NGNN_REQUIRE(dev >= 0 && dev < 64, NGNN_E_UNSUPPORTED, "sage_step: device ordinal %d out of range", dev);
+  AuxCtx& a = g_auxs[dev];
+  if (a.stream == nullptr) {
+    NGNN_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    NGNN_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+    NGNN_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+  }
+  *out = &a;
   return NGNN_OK;
 }
 
@@ -158,35 +168,31 @@ size_t ngnn_sage_step_workspace_bytes(const ngnn_sage_model_t* model, int32_t nu
 
 // phase 0: forward + loss + backward (ngnn_sage_step); phase 1: training-mode forward only, activations stay in ws
 // (ngnn_sage_forward); phase 2: backward only from a caller-supplied top-layer gradient (ngnn_sage_backward).
-static int32_t sage_step_impl(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
-                              const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
+//
+// Extents.  Host mode (block->counts == NULL): the per-hop extents come from block->hop_nodes / hop_edges and every kernel
+// is launched for exactly those sizes.  Device mode (block->counts != NULL): the extents stay in the sampler's device-side
+// `counts`, every launch is sized for the declared capacities (max_hop_*) and reads its row count on the device, so the
+// launch sequence is the same for every block and the whole step can be captured once in a CUDA graph and replayed.
+static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                              const StepPlan& pl, const float* table, int64_t ld_table,
                               const int64_t* target_global, const int64_t* label_global, uint64_t drop_seed, uint64_t drop_offset,
-                              float* stats, float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream,
-                              int32_t phase, const float* dlogits_in, int64_t ld_dlogits) {
-  NGNN_REQUIRE(model && params && block && table && ws && (stats || phase != 0), NGNN_E_INVALID, "sage_step: null pointer");
-  NGNN_REQUIRE(block->rowptr && block->col && block->col_global && block->n_id && block->hop_nodes && block->hop_edges,
-               NGNN_E_INVALID, "sage_step: incomplete block");
-  NGNN_REQUIRE(model->dropout >= 0.f && model->dropout < 1.f, NGNN_E_INVALID, "sage_step: dropout outside [0,1)");
-  StepPlan pl;
-  NGNN_REQUIRE(make_plan(model, block->num_hops, max_hop_nodes, max_hop_edges, block->hop_nodes, block->hop_edges, pl),
-               NGNN_E_INVALID, "sage_step: bad model / block extents (block larger than the declared capacity?)");
-  NGNN_REQUIRE(ws_bytes >= pl.total, NGNN_E_WORKSPACE, "sage_step: workspace too small (%zu < %zu)", ws_bytes, pl.total);
-  NGNN_REQUIRE(ld_table >= model->in_dim, NGNN_E_INVALID, "sage_step: ld_table < in_dim");
-  const bool train = grads != nullptr || phase != 0;
-  NGNN_REQUIRE(!train || phase != 0 || target_global != nullptr, NGNN_E_INVALID, "sage_step: training needs targets");
-  NGNN_REQUIRE(phase != 2 || (grads != nullptr && dlogits_in != nullptr && ld_dlogits >= model->out_dim), NGNN_E_INVALID,
-               "sage_backward: needs the gradient bucket and dlogits");
-  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(ws), 256));
+                              float* stats, float* logits_out, int64_t ld_logits, char* base, ngnn_stream_t stream,
+                              int32_t phase, const float* dlogits_in, int64_t ld_dlogits, AuxCtx* aux, bool& aux_used) {
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   auto I32 = [&](size_t off) { return reinterpret_cast<int32_t*>(base + off); };
   const int L = pl.L;
-  const int64_t bs = block->hop_nodes[0];
+  const bool dev = block->counts != nullptr;
+  const int H = block->num_hops;
+  const int64_t bs = dev ? block->batch_size : block->hop_nodes[0];
+  const bool train = grads != nullptr || phase != 0;
   const float p_drop = (train && model->training) ? model->dropout : 0.f;
+  const StepCtl* ctl = reinterpret_cast<const StepCtl*>(block->ctl);
+  cudaStream_t st = as_stream(stream);
+  // extent of "nodes within hop a" / "edges within hop b" for a kernel: device word + capacity, or the host value
+  auto nodes_ext = [&](int a, int64_t cap, int64_t host) { return dev ? ext_dev(block->counts + a, cap) : ext_host(host); };
   int32_t rc;
 
   // ---------------- split weight planes of every layer: ONE launch, before the step's first kernel ----------------
-  const bool use_aux = g_use_aux && L > 1;
-  if (use_aux) { rc = ensure_aux(); if (rc != NGNN_OK) return rc; }
   bool prep_fwd_ok[16], prep_dg_ok[16];
   prep_batch_begin();
   for (int i = 0; i < L; ++i) {
@@ -202,114 +208,156 @@ static int32_t sage_step_impl(const ngnn_sage_model_t* model, const float* param
     }
   }
   if (phase != 2) {          // phase 2: the planes of the matching forward call are still valid (weights unchanged)
-    rc = prep_batch_launch(as_stream(stream));
+    rc = prep_batch_launch(st);
     if (rc != NGNN_OK) return rc;
   }
 
   // ---------------- forward ----------------
   for (int i = 0; i < L && phase != 2; ++i) {
     const LayerPlan& lp = pl.layer[i];
+    const Ext n_dst = nodes_ext(lp.a, lp.n_dst_max, lp.n_dst);
     const float* root;
     int64_t ld_root;
     if (i == 0) {   // aggregate from the resident table by global ids; gather the root rows in the same launch
-      const bool probe = g_probe_n < g_probe_cap;
-      if (probe) cudaEventRecord(g_probe_ev[2 * g_probe_n], as_stream(stream));
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cap);
+      const bool probe = g_probe_n < g_probe_cap && cap == cudaStreamCaptureStatusNone;
+      if (probe) cudaEventRecord(g_probe_ev[2 * g_probe_n], st);
       const bool remapped = block->col_table != nullptr && block->n_table != nullptr;      // table stored hot rows first
-      rc = agg_fwd_table_impl(block->rowptr, remapped ? block->col_table : block->col_global, table, ld_table, lp.n_dst, lp.F,
-                              F32(lp.mean), lp.F, remapped ? block->n_table : block->n_id, F32(lp.root), lp.F,
-                              remapped ? block->hot_rows : -1, as_stream(stream));
-      if (probe) { cudaEventRecord(g_probe_ev[2 * g_probe_n + 1], as_stream(stream)); ++g_probe_n; }
-      root = F32(lp.root); ld_root = lp.F;
+      rc = agg_fwd_table_impl(block->rowptr, remapped ? block->col_table : block->col_global, table, ld_table, n_dst, lp.F,
+                              F32(lp.mean), lp.ldf, remapped ? block->n_table : block->n_id, F32(lp.root), lp.ldf,
+                              remapped ? block->hot_rows : -1, st);
+      if (probe) { cudaEventRecord(g_probe_ev[2 * g_probe_n + 1], st); ++g_probe_n; }
+      root = F32(lp.root); ld_root = lp.ldf;
     } else {
       const LayerPlan& prev = pl.layer[i - 1];
-      rc = ngnn_sage_agg_fwd(block->rowptr, block->col, F32(prev.out), prev.ldo, lp.n_dst, lp.F, F32(lp.mean), lp.F, nullptr,
-                             nullptr, 0, stream);
+      rc = agg_fwd_impl(block->rowptr, block->col, F32(prev.out), prev.ldo, n_dst, lp.F, F32(lp.mean), lp.ldf, st);
       root = F32(prev.out); ld_root = prev.ldo;
     }
     if (rc != NGNN_OK) return rc;
     const bool last = i == L - 1;
-    rc = gemm_fwd_impl(F32(lp.mean), lp.F, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
-                       lp.n_dst, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
+    rc = gemm_fwd_impl(F32(lp.mean), lp.ldf, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
+                       n_dst.cap, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
                        drop_offset + (uint64_t)i, F32(lp.out), lp.ldo, nullptr, base + lp.prep_fwd, lp.prep_fwd_bytes,
-                       as_stream(stream), prep_fwd_ok[i]);
+                       st, prep_fwd_ok[i], n_dst.dev, ctl, (uint32_t)i);
     if (rc != NGNN_OK) return rc;
   }
   const LayerPlan& top = pl.layer[L - 1];
   if (logits_out && phase != 2) {
     NGNN_REQUIRE(ld_logits >= top.O, NGNN_E_INVALID, "sage_step: ld_logits < out_dim");
     NGNN_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)ld_logits * 4, F32(top.out), (size_t)top.ldo * 4, (size_t)top.O * 4, (size_t)bs,
-                                cudaMemcpyDeviceToDevice, as_stream(stream)));
+                                cudaMemcpyDeviceToDevice, st));
   }
   if (phase == 1) return NGNN_OK;                 // forward of a split step: the caller computes the loss gradient
   if (phase == 2) {                               // top-layer gradient supplied by the caller (e.g. the co-teaching loss)
     NGNN_CUDA(cudaMemcpy2DAsync(F32(top.dy), (size_t)top.ldo * 4, dlogits_in, (size_t)ld_dlogits * 4, (size_t)top.O * 4,
-                                (size_t)bs, cudaMemcpyDeviceToDevice, as_stream(stream)));
+                                (size_t)bs, cudaMemcpyDeviceToDevice, st));
   } else {
     if (target_global == nullptr) return NGNN_OK;   // inference: forward only
 
     // ---------------- loss on the seed rows (labels gathered by global id) ----------------
-    rc = ngnn_ce_fwd_bwd_gather(F32(top.out), top.ldo, target_global, label_global, block->n_id, bs, top.O, 1.0f, stats,
-                                train ? F32(top.dy) : nullptr, top.ldo, F32(pl.ce_rows), stream);
+    rc = ce_impl(F32(top.out), top.ldo, target_global, label_global, block->n_id, bs, top.O, 1.0f, stats,
+                 train ? F32(top.dy) : nullptr, top.ldo, F32(pl.ce_rows), ctl, st);
     if (rc != NGNN_OK) return rc;
     if (!train) return NGNN_OK;
   }
 
   // ---------------- backward ----------------
-  bool aux_used = false;
+  const bool use_aux = aux != nullptr;
   for (int i = L - 1; i >= 0; --i) {
     const LayerPlan& lp = pl.layer[i];
     const float* root = i == 0 ? F32(lp.root) : F32(pl.layer[i - 1].out);
-    const int64_t ld_root = i == 0 ? lp.F : pl.layer[i - 1].ldo;
+    const int64_t ld_root = i == 0 ? lp.ldf : pl.layer[i - 1].ldo;
     // only the first bs rows of the top layer carry a gradient
-    const int64_t n_rows = i == L - 1 ? bs : lp.n_dst;
+    const Ext n_rows = i == L - 1 ? ext_host(bs) : nodes_ext(lp.a, lp.n_dst_max, lp.n_dst);
     if (use_aux && i > 0) {    // fork: dY_i is complete on the main stream here
-      NGNN_CUDA(cudaEventRecord(g_fork, as_stream(stream)));
-      NGNN_CUDA(cudaStreamWaitEvent(g_aux, g_fork, 0));
-      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
-                           grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes, g_aux);
+      NGNN_CUDA(cudaEventRecord(aux->fork, st));
+      NGNN_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
       aux_used = true;
+      rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
+                      grads + lp.off_wl, grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes,
+                      aux->stream);
     } else if (use_aux) {      // layer 1 closes the step: its bias gradient (column sums of dY) runs beside the tensor-core kernel
-      NGNN_CUDA(cudaEventRecord(g_fork, as_stream(stream)));
-      NGNN_CUDA(cudaStreamWaitEvent(g_aux, g_fork, 0));
-      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, nullptr, 0, nullptr, 0, n_rows, lp.F, lp.O, nullptr, nullptr, grads + lp.off_b, 0,
-                           base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes, g_aux);
-      if (rc != NGNN_OK) return rc;
+      NGNN_CUDA(cudaEventRecord(aux->fork, st));
+      NGNN_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
       aux_used = true;
-      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
-                           grads + lp.off_wr, nullptr, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
+      rc = wgrad_impl(F32(lp.dy), lp.ldo, nullptr, 0, nullptr, 0, n_rows.cap, n_rows.dev, lp.F, lp.O, nullptr, nullptr,
+                      grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes, aux->stream);
+      if (rc != NGNN_OK) return rc;
+      rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
+                      grads + lp.off_wl, grads + lp.off_wr, nullptr, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, st);
     } else {
-      rc = ngnn_sage_wgrad(F32(lp.dy), lp.ldo, F32(lp.mean), lp.F, root, ld_root, n_rows, lp.F, lp.O, grads + lp.off_wl,
-                           grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, stream);
+      rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
+                      grads + lp.off_wl, grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, st);
     }
     if (rc != NGNN_OK) return rc;
     if (i == 0) break;   // features are leaves: no data gradient for layer 1
     const LayerPlan& prev = pl.layer[i - 1];
-    const int64_t e_lim = i == L - 1 ? block->hop_edges[1 < block->num_hops ? 1 : block->num_hops] : lp.e_lim;
-    rc = dgrad_impl(F32(lp.dy), lp.ldo, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows, lp.F, lp.O,
-                    F32(pl.dmean), lp.F, F32(pl.droot), lp.F, base + lp.prep_dg, lp.prep_dg_bytes, as_stream(stream),
-                    prep_dg_ok[i]);
+    rc = dgrad_impl(F32(lp.dy), lp.ldo, params + lp.off_wl, params + lp.off_wr, block->rowptr, n_rows.cap, lp.F, lp.O,
+                    F32(pl.dmean), lp.ldf, F32(pl.droot), lp.ldf, base + lp.prep_dg, lp.prep_dg_bytes, st, prep_dg_ok[i], n_rows.dev);
     if (rc != NGNN_OK) return rc;
     const int32_t* colptr_t = I32(lp.colptr_t);
     const int32_t* row_t = I32(lp.row_t);
-    const int hop_b = (L - 1 - i) + 1 < block->num_hops ? (L - 1 - i) + 1 : block->num_hops;   // hop prefix this layer's edges span
+    const int hop_b = lp.b;                             // hop prefix this layer's edges span
     if (hop_b < 8 && block->colptr_t[hop_b] != nullptr && block->row_t[hop_b] != nullptr) {
-      colptr_t = block->colptr_t[hop_b];           // built by the loader on its side stream
+      colptr_t = block->colptr_t[hop_b];           // built by the sampler (or by the loader on its side stream)
       row_t = block->row_t[hop_b];
     } else {
-      rc = ngnn_csr_transpose(block->rowptr, block->col, n_rows, e_lim, lp.n_src, I32(lp.colptr_t), I32(lp.row_t), I32(lp.perm_t),
+      NGNN_REQUIRE(!dev, NGNN_E_INVALID, "sage_step: device-side extents need the block's transposes (colptr_t[%d] / row_t[%d])",
+                   hop_b, hop_b);
+      const int64_t e_lim = i == L - 1 ? block->hop_edges[1 < H ? 1 : H] : lp.e_lim;
+      rc = ngnn_csr_transpose(block->rowptr, block->col, n_rows.cap, e_lim, lp.n_src, I32(lp.colptr_t), I32(lp.row_t), I32(lp.perm_t),
                               base + pl.sort_ws, pl.sort_ws_bytes, stream);
       if (rc != NGNN_OK) return rc;
     }
     // dY of the previous layer = gate(prev output) * (transpose-sum of dmean + droot on the root rows)
-    rc = ngnn_sage_agg_bwd(colptr_t, row_t, F32(pl.dmean), lp.F, lp.n_src, lp.F, F32(pl.droot), lp.F, n_rows,
-                           F32(prev.out), prev.ldo, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.ldo, stream);
+    rc = agg_bwd_impl(colptr_t, row_t, F32(pl.dmean), lp.ldf, nodes_ext(lp.b, lp.n_src_max, lp.n_src), lp.F, F32(pl.droot), lp.ldf,
+                      n_rows, F32(prev.out), prev.ldo, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.ldo, st);
     if (rc != NGNN_OK) return rc;
   }
-  if (aux_used) {            // join: the caller's stream continues only after every weight gradient has landed
-    NGNN_CUDA(cudaEventRecord(g_join, g_aux));
-    NGNN_CUDA(cudaStreamWaitEvent(as_stream(stream), g_join, 0));
-  }
   return NGNN_OK;
+}
+
+static int32_t sage_step_impl(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,
+                              const int64_t* max_hop_nodes, const int64_t* max_hop_edges, const float* table, int64_t ld_table,
+                              const int64_t* target_global, const int64_t* label_global, uint64_t drop_seed, uint64_t drop_offset,
+                              float* stats, float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream,
+                              int32_t phase, const float* dlogits_in, int64_t ld_dlogits) {
+  NGNN_REQUIRE(model && params && block && table && ws && (stats || phase != 0), NGNN_E_INVALID, "sage_step: null pointer");
+  NGNN_REQUIRE(block->rowptr && block->col && block->col_global && block->n_id, NGNN_E_INVALID, "sage_step: incomplete block");
+  const bool dev = block->counts != nullptr;
+  NGNN_REQUIRE(dev || (block->hop_nodes && block->hop_edges), NGNN_E_INVALID, "sage_step: the block carries no extents");
+  NGNN_REQUIRE(!dev || block->batch_size > 0, NGNN_E_INVALID, "sage_step: device-side extents need block->batch_size");
+  NGNN_REQUIRE(model->dropout >= 0.f && model->dropout < 1.f, NGNN_E_INVALID, "sage_step: dropout outside [0,1)");
+  StepPlan pl;
+  NGNN_REQUIRE(make_plan(model, block->num_hops, max_hop_nodes, max_hop_edges, dev ? nullptr : block->hop_nodes,
+                         dev ? nullptr : block->hop_edges, pl),
+               NGNN_E_INVALID, "sage_step: bad model / block extents (block larger than the declared capacity?)");
+  NGNN_REQUIRE(!dev || block->batch_size <= max_hop_nodes[0], NGNN_E_INVALID, "sage_step: batch_size above the declared capacity");
+  NGNN_REQUIRE(ws_bytes >= pl.total, NGNN_E_WORKSPACE, "sage_step: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+  NGNN_REQUIRE(ld_table >= model->in_dim, NGNN_E_INVALID, "sage_step: ld_table < in_dim");
+  const bool train = grads != nullptr || phase != 0;
+  NGNN_REQUIRE(!train || phase != 0 || target_global != nullptr, NGNN_E_INVALID, "sage_step: training needs targets");
+  NGNN_REQUIRE(phase != 2 || (grads != nullptr && dlogits_in != nullptr && ld_dlogits >= model->out_dim), NGNN_E_INVALID,
+               "sage_backward: needs the gradient bucket and dlogits");
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  AuxCtx* aux = nullptr;
+  if (g_use_aux && pl.L > 1 && train && phase != 1) {
+    const int32_t rc = ensure_aux(&aux);
+    if (rc != NGNN_OK) return rc;
+  }
+  bool aux_used = false;
+  const int32_t rc = sage_step_body(model, params, grads, block, pl, table, ld_table, target_global, label_global, drop_seed,
+                                    drop_offset, stats, logits_out, ld_logits, base, stream, phase, dlogits_in, ld_dlogits, aux,
+                                    aux_used);
+  if (aux_used) {   // join on EVERY path (also a failed one): the caller's stream continues only after the auxiliary stream's work —
+                    // a forked stream left dangling would also break an enclosing graph capture
+    cudaError_t e1 = cudaEventRecord(aux->join, aux->stream);
+    cudaError_t e2 = cudaStreamWaitEvent(as_stream(stream), aux->join, 0);
+    if (rc == NGNN_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
+      return set_error(NGNN_E_CUDA, "sage_step: joining the auxiliary stream failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  return rc;
 }
 
 int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,

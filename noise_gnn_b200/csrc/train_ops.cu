@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(256) k_ce_rows(const float* __restrict__ logit
                                                  const int64_t* __restrict__ target, const int64_t* __restrict__ y_true,
                                                  const int32_t* __restrict__ row_ids, int64_t bs, int64_t C,
                                                  float grad_scale, float* __restrict__ rows,
-                                                 float* __restrict__ dlogits, int64_t ld_d) {
+                                                 float* __restrict__ dlogits, int64_t ld_d, const StepCtl* ctl) {
+  if (ctl != nullptr) grad_scale *= __uint_as_float(ctl->loss_scale_bits);     // data-parallel weight of this rank's batch
   const int lane = threadIdx.x & 31;
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (i >= bs) return;
@@ -62,7 +63,9 @@ __global__ void __launch_bounds__(256) k_ce_rows(const float* __restrict__ logit
 }
 
 // Single CTA: fixed-order tree sum of the per-row values => bitwise reproducible loss.
-__global__ void __launch_bounds__(1024) k_ce_reduce(const float* __restrict__ rows, int64_t bs, float* __restrict__ stats) {
+__global__ void __launch_bounds__(1024) k_ce_reduce(const float* __restrict__ rows, int64_t bs, float* __restrict__ stats,
+                                                    const StepCtl* ctl) {
+  if (ctl != nullptr && __uint_as_float(ctl->loss_scale_bits) == 0.f) return;   // a padded (masked-out) batch is not logged
   __shared__ float s_l[1024];
   __shared__ float s_c[1024];
   float l = 0.f, c = 0.f;
@@ -227,19 +230,32 @@ using namespace ngnn;
 
 extern "C" {
 
-int32_t ngnn_ce_fwd_bwd_gather(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true,
-                               const int32_t* row_ids, int64_t bs, int64_t C, float grad_scale, float* stats, float* dlogits,
-                               int64_t ld_d, float* row_scratch, ngnn_stream_t stream) {
+}  // extern "C"
+
+namespace ngnn {
+int32_t ce_impl(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true, const int32_t* row_ids,
+                int64_t bs, int64_t C, float grad_scale, float* stats, float* dlogits, int64_t ld_d, float* row_scratch,
+                const StepCtl* ctl, cudaStream_t st) {
   NGNN_REQUIRE(bs >= 0 && C >= 0, NGNN_E_INVALID, "ce: negative size");
   if (bs == 0 || C == 0) return NGNN_OK;
   NGNN_REQUIRE(logits && target && stats && row_scratch, NGNN_E_INVALID, "ce: null pointer");
   NGNN_REQUIRE(ld >= C && (dlogits == nullptr || ld_d >= C), NGNN_E_INVALID, "ce: leading dimension < C");
-  k_ce_rows<<<(unsigned)ceil_div(bs * 32, 256), 256, 0, as_stream(stream)>>>(logits, ld, target, y_true, row_ids, bs, C,
-                                                                               grad_scale, row_scratch, dlogits, ld_d);
+  k_ce_rows<<<(unsigned)ceil_div(bs * 32, 256), 256, 0, st>>>(logits, ld, target, y_true, row_ids, bs, C, grad_scale, row_scratch,
+                                                                dlogits, ld_d, ctl);
   NGNN_LAUNCH_CHECK();
-  k_ce_reduce<<<1, 1024, 0, as_stream(stream)>>>(row_scratch, bs, stats);
+  k_ce_reduce<<<1, 1024, 0, st>>>(row_scratch, bs, stats, ctl);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;
+}
+}  // namespace ngnn
+
+extern "C" {
+
+int32_t ngnn_ce_fwd_bwd_gather(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true,
+                               const int32_t* row_ids, int64_t bs, int64_t C, float grad_scale, float* stats, float* dlogits,
+                               int64_t ld_d, float* row_scratch, ngnn_stream_t stream) {
+  return ce_impl(logits, ld, target, y_true, row_ids, bs, C, grad_scale, stats, dlogits, ld_d, row_scratch, nullptr,
+                 as_stream(stream));
 }
 
 int32_t ngnn_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* target, const int64_t* y_true, int64_t bs,

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -152,6 +153,41 @@ class Batch:
                 f"hops={self.num_sampled_nodes})")
 
 
+class BlockSlot:
+    """Device buffers of ONE sampled block at the loader's worst-case capacity: allocated once and reused, so that sampling
+    is a fixed launch sequence over fixed addresses (no allocation per batch, capturable in a CUDA graph).  ``trans`` holds
+    the CSC transposes of the hop prefixes 1..T the backward reads (built by the sampler itself)."""
+
+    def __init__(self, loader: "NeighborLoader", transposes: int):
+        dev, H = loader.device, len(loader._fan_cap)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.n_id = torch.empty(loader.max_nodes, **i32)
+        self.rowptr = torch.empty(loader.max_nodes + 1, **i32)
+        self.col = torch.empty(max(loader.max_edges, 1), **i32)
+        self.colg = torch.empty(max(loader.max_edges, 1), **i32)
+        self.epos = torch.empty(max(loader.max_edges, 1), **i32) if loader.return_e_id else None
+        self.edst = torch.empty(max(loader.max_edges, 1), **i32)          # local destination id of every sampled edge
+        self.counts = torch.zeros(2 * (H + 1), **i32)
+        self.colt = torch.empty(max(loader.max_edges, 1), **i32) if loader.remap is not None else None
+        self.nt = torch.empty(loader.max_nodes, **i32) if loader.remap is not None else None
+        self.seeds = torch.zeros(loader.batch_size, dtype=torch.int64, device=dev)
+        self.ctl = torch.zeros(8, **i32)                       # ngnn_step_ctl_t
+        self.trans = []
+        self.ensure_transposes(loader, transposes)
+        self.owner = None                                      # weakref to the Batch handed out on these buffers
+        self.pending = False                                   # sampled into, Batch not created yet
+        self.host_counts = torch.empty(2 * (H + 1), dtype=torch.int32, pin_memory=True)
+
+    def ensure_transposes(self, loader, transposes: int):
+        i32 = dict(dtype=torch.int32, device=loader.device)
+        while len(self.trans) < transposes:
+            b = len(self.trans) + 1
+            self.trans.append((torch.empty(loader.cap_nodes[b] + 1, **i32), torch.empty(max(loader.cap_edges[b], 1), **i32)))
+        T = len(self.trans)
+        self._colptr_t = (ctypes.c_void_p * max(T, 1))(*[t[0].data_ptr() for t in self.trans])
+        self._row_t = (ctypes.c_void_p * max(T, 1))(*[t[1].data_ptr() for t in self.trans])
+
+
 class NeighborLoader:
     def __init__(self, data, num_neighbors: Sequence[int], input_nodes=None, batch_size: int = 1,
                  shuffle: bool = False, replace: bool = False, num_workers: int = 0,
@@ -199,7 +235,7 @@ class NeighborLoader:
                     # at stride 448 it is exactly 7.  The tensor keeps its [N, F] shape; only stride(0) changes.
                     F_ = int(v.size(1)) if v.dim() == 2 else 1
                     ldp = (F_ + 15) // 16 * 16
-                    buf = torch.empty((N, ldp), dtype=torch.float32, device=self.device)
+                    buf = torch.zeros((N, ldp), dtype=torch.float32, device=self.device)   # pad columns stay zero
                     self.x = buf[:, :F_] if v.dim() == 2 else buf
                     self.x.copy_(v.reshape(N, -1).to(self.device, dtype=torch.float32))
                 else:
@@ -220,7 +256,7 @@ class NeighborLoader:
                 self.remap = torch.empty(N, dtype=torch.int32, device=self.device)
                 self.remap[order] = torch.arange(N, dtype=torch.int32, device=self.device)
                 ldp = self.x.stride(0)
-                buf = torch.empty((N, ldp), dtype=torch.float32, device=self.device)
+                buf = torch.zeros((N, ldp), dtype=torch.float32, device=self.device)   # pad columns stay zero
                 self.x_hot = buf[:, :self.x.size(1)]
                 self.x_hot.copy_(self.x.index_select(0, order))
                 self.hot_rows = int(min(N, hot_feature_bytes // (ldp * 4)))
@@ -233,6 +269,8 @@ class NeighborLoader:
                 if nodes.dtype == torch.bool:
                     nodes = nodes.nonzero().view(-1)
                 nodes = nodes.to(torch.int64).view(-1)
+            if nodes.numel() and (int(nodes.min()) < 0 or int(nodes.max()) >= N):
+                raise ValueError(f"input_nodes must lie in [0, {N}): got ids in [{int(nodes.min())}, {int(nodes.max())}]")
             self.input_nodes = nodes
             self.sharder = SeedSharder(nodes, self.batch_size, self.shuffle, self.seed, self.rank, self.world_size,
                                        self.drop_last)
@@ -244,6 +282,13 @@ class NeighborLoader:
             _lib.call("ngnn_sample_capacity", self.batch_size, self._fan, len(self.num_neighbors), N,
                       ctypes.byref(mn), ctypes.byref(me))
             self.max_nodes, self.max_edges = mn.value, me.value
+            # cumulative worst-case nodes / edges after each hop (capacities of the transposed prefixes, arena sizing)
+            self.cap_nodes, self.cap_edges = [self.batch_size], [0]
+            for h in range(1, len(self.num_neighbors) + 1):
+                _lib.call("ngnn_sample_capacity", self.batch_size, self._fan, h, N, ctypes.byref(mn), ctypes.byref(me))
+                self.cap_nodes.append(mn.value)
+                self.cap_edges.append(me.value)
+            self._slots = []
             nbytes = L.ngnn_sample_workspace_bytes(N, self.batch_size, self._fan, len(self.num_neighbors))
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             _lib.call("ngnn_sample_workspace_init", ops._ptr(self._ws), self._ws.numel(), N, ops._stream())
@@ -283,63 +328,98 @@ class NeighborLoader:
         return cache[name][1]
 
     # ------------------------------------------------------------------ sampling
-    def _launch_sample(self, seeds: torch.Tensor, epoch: int, batch_idx: int):
-        """Enqueue one ngnn_sample_block on the CURRENT stream; returns the pending pieces (no host sync)."""
+    def _acquire_slot(self) -> "BlockSlot":
+        """A BlockSlot no live Batch refers to (grows the pool when every slot is still held by the consumer)."""
+        for slot in self._slots:
+            if not slot.pending and (slot.owner is None or slot.owner() is None):
+                slot.ensure_transposes(self, self.transpose_hops)
+                slot.pending = True
+                return slot
+        slot = BlockSlot(self, self.transpose_hops)
+        slot.pending = True
+        self._slots.append(slot)
+        return slot
+
+    def fixed_slots(self, count: int, transposes: int):
+        """`count` dedicated BlockSlots for a captured step (noise_gnn_b200.train.Trainer): their addresses never change."""
+        cache = self.__dict__.setdefault("_fixed_slots", [])
+        while len(cache) < count:
+            cache.append(BlockSlot(self, transposes))
+        for slot in cache:
+            slot.ensure_transposes(self, transposes)
+        return cache[:count]
+
+    def launch_sample(self, slot: "BlockSlot", seeds: Optional[torch.Tensor], bs: int, epoch: int, batch_idx: int,
+                      use_ctl: bool = False, transposes: Optional[int] = None):
+        """Enqueue one ngnn_sample_block_ex into `slot` on the CURRENT stream (no host sync, no allocation).  `seeds`: int64
+        host (pinned) or device tensor copied into the slot's seed buffer, or None when the caller already filled it.
+        use_ctl: the RNG key is read from the slot's device-side control words (set with ngnn_step_ctl_set) instead of
+        (epoch, batch_idx) — what a captured launch sequence needs."""
         H = len(self.num_neighbors)
-        if not seeds.is_cuda:
-            seeds = (seeds if seeds.is_pinned() else seeds.pin_memory()).to(self.device, non_blocking=True)
-        seeds = seeds.to(torch.int64).contiguous()
-        bs = seeds.numel()
-        if bs == 0:
+        if bs <= 0:
             raise ValueError("cannot sample an empty seed batch")
         if bs > self.batch_size:
             raise ValueError(f"{bs} seeds exceed the loader's batch_size {self.batch_size}")
-        dev = self.device
-        n_id = torch.empty(self.max_nodes, dtype=torch.int32, device=dev)
-        rowptr = torch.empty(self.max_nodes + 1, dtype=torch.int32, device=dev)
-        col = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
-        colg = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
-        epos = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev) if self.return_e_id else None
-        counts = torch.empty(2 * (H + 1), dtype=torch.int32, device=dev)
+        if seeds is not None:
+            slot.seeds[:bs].copy_(seeds.view(-1)[:bs], non_blocking=True)
+        T = len(slot.trans) if transposes is None else min(int(transposes), len(slot.trans))
+        T = min(T, H)
         with ops._timed("sample"):
-            _lib.call("ngnn_sample_block", ops._ptr(self.colptr), ops._ptr(self.row), self.num_nodes, ops._ptr(seeds), bs,
+            _lib.call("ngnn_sample_block_ex", ops._ptr(self.colptr), ops._ptr(self.row), self.num_nodes, ops._ptr(slot.seeds), bs,
                       self._fan, H, int(self.replace), self.seed & (2**64 - 1), epoch & 0xFFFFFFFF, batch_idx & 0xFFFFFFFF,
-                      ops._ptr(n_id), ops._ptr(rowptr), ops._ptr(col), ops._ptr(colg), ops._ptr(epos), ops._ptr(counts),
+                      ops._ptr(slot.ctl) if use_ctl else None, ops._ptr(slot.n_id), ops._ptr(slot.rowptr), ops._ptr(slot.col),
+                      ops._ptr(slot.colg), ops._ptr(slot.epos), ops._ptr(slot.edst), ops._ptr(slot.counts), T, slot._colptr_t,
+                      slot._row_t,
                       ops._ptr(self._ws), self._ws.numel(), ops._stream())
-        colt = nt = None
         if self.remap is not None:                        # table rows of the block (same stream, no host round trip)
-            colt = torch.empty(max(self.max_edges, 1), dtype=torch.int32, device=dev)
-            nt = torch.empty(self.max_nodes, dtype=torch.int32, device=dev)
-            _lib.call("ngnn_block_table_index", ops._ptr(self.remap), ops._ptr(colg), ops._ptr(n_id), ops._ptr(counts), H,
-                      self.max_nodes, self.max_edges, ops._ptr(colt), ops._ptr(nt), ops._stream())
-        host_counts = torch.empty(2 * (H + 1), dtype=torch.int32, pin_memory=True)
-        host_counts.copy_(counts, non_blocking=True)      # the one device->host read per batch: block extents
-        return dict(seeds=seeds, bs=bs, n_id=n_id, rowptr=rowptr, col=col, colg=colg, epos=epos, counts=counts,
-                    host_counts=host_counts, colt=colt, nt=nt)
+            _lib.call("ngnn_block_table_index", ops._ptr(self.remap), ops._ptr(slot.colg), ops._ptr(slot.n_id), ops._ptr(slot.counts),
+                      H, self.max_nodes, self.max_edges, ops._ptr(slot.colt), ops._ptr(slot.nt), ops._stream())
+        return T
+
+    def _launch_sample(self, seeds: torch.Tensor, epoch: int, batch_idx: int):
+        """Sample into a free slot on the CURRENT stream and start the (asynchronous) read of its extents."""
+        if not seeds.is_cuda and not seeds.is_pinned():
+            seeds = seeds.pin_memory()
+        seeds = seeds.to(torch.int64)
+        bs = seeds.numel()
+        slot = self._acquire_slot()
+        T = self.launch_sample(slot, seeds, bs, epoch, batch_idx)
+        slot.host_counts.copy_(slot.counts, non_blocking=True)      # the one device->host read per batch: block extents
+        return dict(slot=slot, bs=bs, T=T)
 
     def _finish_sample(self, pend) -> Batch:
         H = len(self.num_neighbors)
-        c = pend["host_counts"].tolist()
-        hop_nodes, hop_edges = c[:H + 1], c[H + 1:]
+        slot = pend["slot"]
+        c = slot.host_counts.tolist()
+        hop_nodes, hop_edges = c[:H + 1], c[H + 1:2 * (H + 1)]
         n, e = hop_nodes[-1], hop_edges[-1]
-        block = ops.Block(pend["rowptr"][:n + 1], pend["col"][:e], n, e, hop_nodes=hop_nodes, hop_edges=hop_edges,
-                          col_global=pend["colg"][:e], n_id=pend["n_id"][:n])
-        if pend.get("colt") is not None:
-            block.col_table, block.n_table = pend["colt"][:e], pend["nt"][:n]
-        epos = pend["epos"]
-        return Batch(self, block, pend["n_id"][:n], None if epos is None else epos[:e], pend["bs"], pend["seeds"])
+        block = ops.Block(slot.rowptr[:n + 1], slot.col[:e], n, e, hop_nodes=hop_nodes, hop_edges=hop_edges,
+                          col_global=slot.colg[:e], n_id=slot.n_id[:n])
+        block.counts = slot.counts
+        for b in range(1, pend["T"] + 1):                 # transposes built by the sampler
+            block._t[(hop_edges[b], hop_nodes[b])] = (slot.trans[b - 1][0][:hop_nodes[b] + 1], slot.trans[b - 1][1][:hop_edges[b]])
+        if slot.colt is not None:
+            block.col_table, block.n_table = slot.colt[:e], slot.nt[:n]
+        batch = Batch(self, block, slot.n_id[:n], None if slot.epos is None else slot.epos[:e], pend["bs"], slot.seeds[:pend["bs"]])
+        batch._slot = slot
+        slot.owner = weakref.ref(batch)
+        slot.pending = False
+        return batch
 
     def sample(self, seeds: torch.Tensor, epoch: int = 0, batch_idx: int = 0) -> Batch:
         """Sample one block for explicit seeds (host or device int64) on the current stream."""
         with torch.cuda.device(self.device):
-            pend = self._launch_sample(seeds, epoch, batch_idx)
+            side = self.__dict__.get("_side")
+            if side is not None:                          # the sampler workspace is shared with the iterator's side stream
+                torch.cuda.current_stream().wait_stream(side)
+            pend = self._launch_sample(torch.as_tensor(seeds), epoch, batch_idx)
             torch.cuda.current_stream().synchronize()
             return self._finish_sample(pend)
 
     def __iter__(self):
-        """Yields device-resident batches.  Sampling runs two blocks ahead on a side stream and the backward's CSC
-        transposes on a second one, so the caller's stream only ever sees the step's own kernels; the host blocks
-        only on the 8-int extents of the batch it is about to hand out (sampled long before)."""
+        """Yields device-resident batches.  Sampling (block + the backward's CSC transposes, one fixed launch sequence) runs
+        up to two blocks ahead on a side stream into pooled buffers; the host blocks only on the extents of the batch it is
+        about to hand out (sampled long before).  A batch's buffers return to the pool when the consumer drops it."""
         epoch = self.epoch
         self.epoch += 1
         order = self.epoch_permutation(epoch)
@@ -347,8 +427,7 @@ class NeighborLoader:
         with torch.cuda.device(self.device):
             if self.__dict__.get("_side") is None:
                 self._side = torch.cuda.Stream(device=self.device)
-                self._side_t = torch.cuda.Stream(device=self.device)
-            side, side_t = self._side, self._side_t
+            side = self._side
             side.wait_stream(torch.cuda.current_stream())          # the resident graph was built on the caller's stream
             order = order.to(self.device) if self.seeds_on_device else order.pin_memory()
             pending = {}
@@ -359,6 +438,8 @@ class NeighborLoader:
                 while state["next"] < min(upto, steps):
                     k = state["next"]
                     g = self.sharder.global_batch_index(k)
+                    # buffers freed by the consumer may still be read by work it enqueued: order the reuse after it
+                    side.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(side):
                         pend = self._launch_sample(self.batch_seeds(order, g), epoch, g)
                         ev = torch.cuda.Event()
@@ -372,25 +453,11 @@ class NeighborLoader:
                 pend, ev = pending.pop(i)
                 ev.synchronize()                                   # host needs the block extents of batch i
                 batch = self._finish_sample(pend)
-                main = torch.cuda.current_stream()
-                if self.transpose_hops > 0:
-                    # the backward's CSC transposes only depend on the block: build them off the step's critical path
-                    blk = batch.block
-                    side_t.wait_event(ev)
-                    with torch.cuda.stream(side_t):
-                        for t in (pend["rowptr"], pend["col"]):
-                            t.record_stream(side_t)
-                        for b in range(1, min(self.transpose_hops, len(blk.hop_nodes) - 1) + 1):
-                            for t in blk.transpose(blk.hop_edges[b], blk.hop_nodes[b]):
-                                t.record_stream(main)
-                        ev = torch.cuda.Event()
-                        ev.record(side_t)
-                main.wait_event(ev)
-                for k in ("seeds", "n_id", "rowptr", "col", "colg", "epos", "counts", "colt", "nt"):
-                    if pend[k] is not None:
-                        pend[k].record_stream(main)                # allocated on the side stream, consumed on main
+                torch.cuda.current_stream().wait_event(ev)
+                del pend
                 # Trainer.train_step calls this right after it has enqueued the step, so the next sampling is queued
                 # while the GPU is busy; a plain consumer gets the same effect when the generator resumes
                 batch._prefetch = lambda upto=i + 3: advance(upto)
                 yield batch
+                del batch
                 advance(i + 3)

@@ -25,7 +25,10 @@ import torch.nn.functional as F
 from . import ops
 from .conv import SAGEConv, _block_cache
 
+import itertools
+
 NGNN_ACT_NONE, NGNN_ACT_RELU = 0, 1
+_instances = itertools.count()
 
 
 class _SAGELayerFunction(torch.autograd.Function):
@@ -84,7 +87,9 @@ class SAGE(torch.nn.Module):
             self.bn1 = torch.nn.BatchNorm1d(in_size)
             self.bn2 = torch.nn.BatchNorm1d(hidden_size)
         self._drop_calls = 0
-        self.drop_seed = 1232
+        # key of the fused (Philox) dropout stream: follows torch's seed, distinct per network instance — two peer networks
+        # of a co-teaching pair must not share their masks (the reference draws them independently from torch's generator)
+        self.drop_seed = (torch.initial_seed() * 1000003 + next(_instances)) & (2**63 - 1)
 
     def reset_parameters(self):
         for conv in self.convs:
@@ -117,8 +122,9 @@ class SAGE(torch.nn.Module):
             ext.append((hn[min(d, H)], he[min(d + 1, H)], hn[min(d + 1, H)]))
         return ext
 
-    def forward_batch(self, batch, x_table=None):
-        """Trimmed fused forward on a Batch of our NeighborLoader; returns logits of the seed rows."""
+    def forward_batch(self, batch, x_table=None, return_hidden: bool = False):
+        """Trimmed fused forward on a Batch of our NeighborLoader; returns logits of the seed rows (and, with
+        return_hidden, the list of every layer's output rows)."""
         if self.use_bn:
             raise NotImplementedError("use_bn is dead code in the reference; the fused path does not cover it")
         block = batch.block
@@ -127,6 +133,7 @@ class SAGE(torch.nn.Module):
         self._drop_calls += 1
         ext = self.layer_extents(block, self.num_layers)
         h = table
+        hidden = []
         last = self.num_layers - 1
         for i, conv in enumerate(self.convs):
             n_dst, e_limit, n_src = ext[i]
@@ -136,7 +143,8 @@ class SAGE(torch.nn.Module):
                                          self._drop_calls * self.num_layers + i, f"l{i + 1}",
                                          (1.0 / (1.0 - p)) if i > 0 else 0.0,   # input = previous layer's relu/dropout output
                                          i != last)                              # the next layer gates this layer's gradient
-        return h[: batch.batch_size]
+            hidden.append(h)
+        return (h[: batch.batch_size], hidden) if return_hidden else h[: batch.batch_size]
 
     # ---- layer-wise inference (reference sage.py:42-58) -----------------------------------------
     @torch.no_grad()

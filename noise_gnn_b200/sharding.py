@@ -4,7 +4,8 @@ The reference is single-process (src/main.py:76-83); its loader draws ``ceil(len
 shuffled batches per epoch (src/pipeline.py:75-83, 152).  For N GPUs the same global batch sequence is dealt
 round-robin: rank r of R trains on global batches r, r+R, r+2R, ...  The epoch order is a pure function of
 (seed, epoch) — identical on every rank with no communication — and the last round wraps around so every rank
-issues the same number of steps (collectives stay matched).
+issues the same number of steps (collectives stay matched); the wrapped batches are weighted 0 (``loss_scale``), and a
+short last batch is weighted by its size, so the all-reduced gradient is the mean over the round's real seeds.
 """
 from __future__ import annotations
 
@@ -42,6 +43,28 @@ class SeedSharder:
     def global_batch_index(self, step: int) -> int:
         """Global batch trained by this rank at local step `step` (wraps around in the last, padded round)."""
         return (step * self.world_size + self.rank) % max(self.num_batches_global, 1)
+
+    def batch_len(self, global_batch_idx: int) -> int:
+        """Number of seeds of a global batch (only the epoch's last batch can be short)."""
+        n = len(self.input_nodes)
+        return max(min(self.batch_size, n - global_batch_idx * self.batch_size), 0)
+
+    def is_padded(self, step: int) -> bool:
+        """True when this rank's batch at local step `step` is a wrap-around filler of the epoch's last, incomplete round: it
+        keeps the collectives matched but must not contribute to the gradient or the logged loss."""
+        return step * self.world_size + self.rank >= self.num_batches_global
+
+    def loss_scale(self, step: int) -> float:
+        """Weight of this rank's mean-loss gradient at local step `step` such that the all-reduced MEAN over the ranks is
+        the mean over the seeds of the whole round (the global batch): bs_r * R / sum_r bs_r over the ranks that hold a real
+        batch; 0 for a padded one.  1.0 on a single rank.  Pure host arithmetic, identical on every rank."""
+        if self.is_padded(step):
+            return 0.0
+        nb = self.num_batches_global
+        lens = [self.batch_len(step * self.world_size + r) for r in range(self.world_size) if step * self.world_size + r < nb]
+        total = sum(lens)
+        mine = self.batch_len(step * self.world_size + self.rank)
+        return float(mine) * self.world_size / float(total) if total > 0 else 0.0
 
     def batch_seeds(self, order: torch.Tensor, global_batch_idx: int) -> torch.Tensor:
         b = global_batch_idx % max(self.num_batches_global, 1)

@@ -71,8 +71,12 @@ class Trainer:
     """Owns the flat buckets, the step arena and the fused optimizer for one SAGE network."""
 
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 process_group=None, world_size: int = 1):
+                 process_group=None, world_size: int = 1, rank: int = 0, use_graph: bool = True):
         self.model = model
+        self.rank, self.use_graph = int(rank), bool(use_graph)
+        self._gs = None                      # captured-step state (see run_steps)
+        self.graph_replays = 0               # steps issued as a graph replay, and the kernel launches those replays contained
+        self.replayed_launches = 0
         self.buckets = FlatBuckets(model)
         dev = self.buckets.param.device
         self.exp_avg = torch.zeros_like(self.buckets.param)
@@ -137,8 +141,8 @@ class Trainer:
     def _ensure_arena(self, loader, ms):
         key = (loader.batch_size, tuple(loader.num_neighbors), loader.num_nodes)
         if self._arena_key != key:
-            nodes, edges = hop_capacities(loader.batch_size, loader.num_neighbors, loader.num_nodes)
             H = len(loader.num_neighbors)
+            nodes, edges = list(loader.cap_nodes[:H + 1]), list(loader.cap_edges[:H + 1])   # the sampler's own worst case
             self._max_nodes = (ctypes.c_int64 * (H + 1))(*nodes)
             self._max_edges = (ctypes.c_int64 * (H + 1))(*edges)
             nbytes = _lib.load().ngnn_sage_step_workspace_bytes(ctypes.byref(ms), H, self._max_nodes, self._max_edges)
@@ -176,10 +180,159 @@ class Trainer:
         with ops._timed("sage_step"):
             _lib.call("ngnn_sage_step", ctypes.byref(ms), ops._ptr(self.buckets.param),
                       ops._ptr(self.buckets.grad) if train else None, ctypes.byref(bd), self._max_nodes, self._max_edges,
-                      ops._ptr(table), table.stride(0), ops._ptr(tgt), ops._ptr(lab), self.model.drop_seed,
+                      ops._ptr(table), table.stride(0), ops._ptr(tgt), ops._ptr(lab), self._drop_seed(),
                       self.steps * self._cfg["num_layers"], ops._ptr(self.stats), ops._ptr(logits),
                       logits.stride(0) if logits is not None else 0, ops._ptr(arena), arena.numel(), ops._stream())
         return logits
+
+    def _drop_seed(self) -> int:
+        """Key of the fused dropout stream: the model's seed, decorrelated across data-parallel ranks."""
+        return (int(self.model.drop_seed) + 0x9E3779B97F4A7C15 * self.rank) & (2**64 - 1)
+
+    # ------------------------------------------------------------------ the epoch loop on a captured step
+    def _graph_state(self, loader, target_attr, label_attr):
+        """Everything a replayed step addresses — two block slots, the arena, the label arrays, the side stream — keyed on
+        what the captured launch sequence bakes in."""
+        tgt = loader.label_array(target_attr)
+        lab = loader.label_array(label_attr) if label_attr else None
+        ms = self._model_struct(training=self.model.training)
+        arena = self._ensure_arena(loader, ms)
+        table = loader.x_hot if loader.x_hot is not None else loader.x
+        key = (id(loader), loader.batch_size, tuple(loader.num_neighbors), tgt.data_ptr(), lab.data_ptr() if lab is not None else 0,
+               bool(self.model.training), float(self.model.dropout), arena.data_ptr(), table.data_ptr(), self.world_size)
+        gs = self._gs
+        if gs is None or gs["key"] != key:
+            H = len(loader.num_neighbors)
+            T = min(self._cfg["num_layers"] - 1, H, 4)
+            gs = dict(key=key, loader=loader, tgt=tgt, lab=lab, ms=ms, arena=arena, table=table, H=H, T=T,
+                      slots=loader.fixed_slots(2, T), side=torch.cuda.Stream(device=arena.device), graphs=[None, None],
+                      graph_launches=[0, 0])
+            self._gs = gs
+        return gs
+
+    def _slot_desc(self, gs, k: int, bs: int):
+        """ngnn_block_t over slot k with DEVICE-side extents (counts), the sampler-built transposes and the control words."""
+        slot, loader = gs["slots"][k], gs["loader"]
+        bd = _lib.BlockDesc(slot.rowptr.data_ptr(), slot.col.data_ptr(), slot.colg.data_ptr(), slot.n_id.data_ptr(), gs["H"], None, None)
+        for b in range(1, gs["T"] + 1):
+            bd.colptr_t[b], bd.row_t[b] = slot.trans[b - 1][0].data_ptr(), slot.trans[b - 1][1].data_ptr()
+        if loader.x_hot is not None:
+            bd.col_table, bd.n_table, bd.hot_rows = slot.colt.data_ptr(), slot.nt.data_ptr(), loader.hot_rows
+        bd.counts, bd.batch_size, bd.ctl = slot.counts.data_ptr(), int(bs), slot.ctl.data_ptr()
+        return bd
+
+    def _enqueue_pair(self, gs, k: int, bs_cur: int, bs_next: int):
+        """step(slot k) on the current stream  ||  sample(next block -> slot 1-k) on the side stream, then all-reduce + Adam.
+        The same call sequence runs eagerly (first steps, ragged tail) and under graph capture."""
+        loader, side = gs["loader"], gs["side"]
+        cur = torch.cuda.current_stream()
+        if bs_next > 0:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                loader.launch_sample(gs["slots"][1 - k], None, bs_next, 0, 0, use_ctl=True, transposes=gs["T"])
+        bd = self._slot_desc(gs, k, bs_cur)
+        ms, arena, table = gs["ms"], gs["arena"], gs["table"]
+        _lib.call("ngnn_sage_step", ctypes.byref(ms), ops._ptr(self.buckets.param), ops._ptr(self.buckets.grad), ctypes.byref(bd),
+                  self._max_nodes, self._max_edges, ops._ptr(table), table.stride(0), ops._ptr(gs["tgt"]), ops._ptr(gs["lab"]),
+                  self._drop_seed(), 0, ops._ptr(self.stats), None, 0, ops._ptr(arena), arena.numel(), ops._stream())
+        self.optimizer_step()
+        if bs_next > 0:
+            cur.wait_stream(side)
+
+    def run_steps(self, loader, n_steps: int, start_epoch: int = 0, start_step: int = 0, target_attr: str = "yhn",
+                  label_attr: Optional[str] = "y", seeds_resident: bool = False, log_every_step: bool = True, on_step=None):
+        """`n_steps` consecutive train steps of this rank's schedule, starting at local step `start_step` of epoch
+        `start_epoch` and continuing across epoch boundaries (each epoch has its own rank-agnostic seed permutation).
+
+        Every step is the SAME launch sequence over fixed buffers — sample the next block (side stream) while the current
+        one runs forward / loss / backward / [all-reduce] / Adam — with all block extents left on the device, so it is
+        captured once per buffer parity in a CUDA graph and replayed: per step the host issues the next block's seed ids
+        (H2D from pinned memory, or a device copy when ``seeds_resident``), one control-word kernel, one graph launch and,
+        with ``log_every_step``, an asynchronous read-back of the loss / accuracy accumulators (the reference reads them
+        every step, src/pipeline.py:164-165).  The first two steps and ragged batches run the same calls eagerly.
+        ``on_step(j)`` is called after step j has been enqueued.
+
+        Returns (sum of step losses, correct seed predictions, per-step cumulative (loss, correct) snapshots or None)."""
+        dev = self.buckets.param.device
+        n_steps = int(n_steps)
+        if n_steps <= 0:
+            return 0.0, 0, None
+        with torch.cuda.device(dev):
+            gs = self._graph_state(loader, target_attr, label_attr)
+            sh = loader.sharder
+            spe = len(loader)                                   # steps per epoch on this rank
+            L = self._cfg["num_layers"]
+            bs_full = loader.batch_size
+            steps0 = self.steps                                 # the step that consumes schedule entry j is number steps0 + j + 1
+            cur = torch.cuda.current_stream()
+            side = loader.__dict__.get("_side")
+            if side is not None:                                # the sampler workspace may still be in use by the loader's own iterator
+                cur.wait_stream(side)
+            orders = {}
+
+            def order_of(epoch):
+                if epoch not in orders:
+                    o = loader.epoch_permutation(epoch)
+                    orders[epoch] = o.to(dev) if seeds_resident else o.pin_memory()
+                return orders[epoch]
+
+            def stage_block(j, k):
+                """seed ids + control words of schedule entry j into slot k (stream-ordered; nothing the host must keep alive)"""
+                epoch, i = start_epoch + (start_step + j) // spe, (start_step + j) % spe
+                g = sh.global_batch_index(i)
+                bs, w = sh.batch_len(g), sh.loss_scale(i)
+                slot = gs["slots"][k]
+                slot.seeds[:bs].copy_(loader.batch_seeds(order_of(epoch), g), non_blocking=True)
+                _lib.call("ngnn_step_ctl_set", ops._ptr(slot.ctl), epoch & 0xFFFFFFFF, g & 0xFFFFFFFF, (steps0 + j + 1) * L, float(w),
+                          ops._stream())
+                return bs
+
+            lib = _lib.load()
+            log = torch.empty((n_steps, 2), dtype=torch.float32, pin_memory=True) if log_every_step else None
+            self.stats.zero_()
+            # prologue: the first block is sampled eagerly into slot 0
+            bs_cur = stage_block(0, 0)
+            loader.launch_sample(gs["slots"][0], None, bs_cur, 0, 0, use_ctl=True, transposes=gs["T"])
+            for j in range(n_steps):
+                k = j & 1
+                bs_next = stage_block(j + 1, 1 - k) if j + 1 < n_steps else 0
+                self.steps += 1
+                full = bs_cur == bs_full and bs_next == bs_full
+                if self.use_graph and full and j >= 2:
+                    if gs["graphs"][k] is None:
+                        c0 = lib.ngnn_launch_count()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._enqueue_pair(gs, k, bs_full, bs_full)
+                        gs["graphs"][k] = g
+                        gs["graph_launches"][k] = int(lib.ngnn_launch_count() - c0)
+                    gs["graphs"][k].replay()
+                    self.graph_replays += 1
+                    self.replayed_launches += gs["graph_launches"][k]
+                else:
+                    self._enqueue_pair(gs, k, bs_cur, bs_next)
+                if log is not None:
+                    log[j].copy_(self.stats, non_blocking=True)
+                if on_step is not None:
+                    on_step(j)
+                bs_cur = bs_next
+            total = self.stats.tolist()                         # one synchronising read at the end
+            return total[0], int(total[1]), log
+
+    def train_epoch(self, loader, target_attr: str = "yhn", label_attr: Optional[str] = "y", epoch: Optional[int] = None,
+                    max_steps: Optional[int] = None, seeds_resident: bool = False, log_every_step: bool = True):
+        """One pass of ``PipelineCO.train`` (reference src/pipeline.py:144-173) over this rank's share of the epoch, on the
+        captured step (see run_steps).  Returns (train_loss = mean step loss as the reference logs it, correct seed
+        predictions, per-step cumulative (loss, correct) snapshots or None)."""
+        if epoch is None:
+            epoch = loader.epoch
+            loader.epoch += 1
+        steps = len(loader) if max_steps is None else min(int(max_steps), len(loader))
+        if steps <= 0:
+            return 0.0, 0, None
+        loss_sum, correct, log = self.run_steps(loader, steps, start_epoch=epoch, target_attr=target_attr, label_attr=label_attr,
+                                                seeds_resident=seeds_resident, log_every_step=log_every_step)
+        return loss_sum / steps, correct, log
 
     def optimizer_step(self):
         bk = self.buckets
@@ -222,7 +375,7 @@ class Trainer:
         table = self._table(loader, batch.block, bd)
         self.steps += 1
         _lib.call("ngnn_sage_forward", ctypes.byref(ms), ops._ptr(self.buckets.param), ctypes.byref(bd), self._max_nodes,
-                  self._max_edges, ops._ptr(table), table.stride(0), self.model.drop_seed,
+                  self._max_edges, ops._ptr(table), table.stride(0), self._drop_seed(),
                   self.steps * self._cfg["num_layers"], ops._ptr(logits), logits.stride(0), ops._ptr(arena), arena.numel(),
                   ops._stream())
         return logits

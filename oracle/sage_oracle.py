@@ -110,13 +110,24 @@ class SAGERef(torch.nn.Module):
         for conv in self.convs:
             conv.reset_parameters()
 
-    def forward(self, x, edge_index, dropout_masks=None):
+    def forward(self, x, edge_index, dropout_masks=None, relu_masks=None):
         """dropout_masks: optional list of keep-masks (one per hidden layer) to replace torch's RNG, so a
-        fused-dropout kernel can be compared on the identical mask."""
+        fused-dropout kernel can be compared on the identical mask.
+        relu_masks: optional list of boolean "pre-activation counted as positive" masks (one per hidden layer; rows beyond a
+        mask's length use the oracle's own sign).  ReLU is discontinuous in its gradient: an fp32 implementation and this
+        fp64 oracle legitimately disagree on the sign of a pre-activation that is zero to rounding, and ONE such element
+        moves a weight gradient of a 77 k-row block by ~1e-3 (its terms cancel to ~1/sqrt(n) of their magnitude).  Gradient
+        parity at scale is therefore taken on identical gates, like dropout parity on identical masks."""
         for i, conv in enumerate(self.convs):
             x = conv(x, edge_index)
             if i != self.num_layers - 1:
-                x = x.relu()
+                if relu_masks is not None:
+                    m = x > 0
+                    r = relu_masks[i]
+                    m[: r.size(0)] = r
+                    x = torch.where(m, x, torch.zeros_like(x))
+                else:
+                    x = x.relu()
                 if dropout_masks is not None:
                     m = dropout_masks[i]
                     x = x * m[: x.size(0)].to(x.dtype) / (1.0 - self.dropout)

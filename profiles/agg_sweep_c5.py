@@ -63,12 +63,19 @@ def one_block(name, fanout, scale=1.0, all_nodes=True, batch=None):
 results = []
 
 
+def padded(rows, F):
+    """[rows, F] fp32 with the row stride rounded up to 4 floats — what the loader's table and the step arena use, so that
+    widths like 767 / 1433 take the 128-bit kernels (the pad columns are never looked at)."""
+    return torch.zeros((rows, (F + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :F]
+
+
+
 def measure(tag, blk, n_dst, e, x, col, root_idx=None):
     """fwd on (rowptr, col) reading rows of x; bwd on the transpose writing n_src rows."""
     F = x.size(1)
     n_src = x.size(0) if root_idx is None and col is blk.col else None
     u = torch.unique(col[:e]).numel()
-    out = torch.empty((n_dst, F), dtype=torch.float32, device=dev)
+    out = padded(n_dst, F)
     t_f = timed(lambda: ops.agg_fwd(blk.rowptr, col, x, n_dst, out=out))
     by_f = 4 * F * u + 4 * e + 4 * (n_dst + 1) + 4 * F * n_dst
     ga_f = 4 * F * e + 4 * e + 4 * (n_dst + 1) + 4 * F * n_dst
@@ -77,8 +84,8 @@ def measure(tag, blk, n_dst, e, x, col, root_idx=None):
            "fwd_gather_gbs": round(ga_f / t_f / 1e6, 1), "fwd_bytes": by_f}
     if n_src is not None:          # local-id block: the backward is defined (sources are block rows)
         colptr_t, row_t = blk.transpose(e, n_src)
-        dmean = torch.randn((n_dst, F), dtype=torch.float32, device=dev)
-        dx = torch.empty((n_src, F), dtype=torch.float32, device=dev)
+        dmean = padded(n_dst, F).normal_()
+        dx = padded(n_src, F)
         t_b = timed(lambda: ops.agg_bwd(colptr_t, row_t, dmean, n_src, out=dx))
         by_b = 4 * F * n_dst + 4 * e + 4 * (n_src + 1) + 4 * F * n_src
         rec.update({"bwd_us": round(t_b * 1e3, 2), "bwd_gbs": round(by_b / t_b / 1e6, 1),
@@ -92,7 +99,7 @@ for fanout in (5, 10, 15, 20, 25):
     blk = b.block
     n, e = blk.n_rows, blk.e
     for F in (64, 128, 256, 512, 767, 1024, 1433):
-        x = torch.randn((n, F), dtype=torch.float32, device=dev)
+        x = padded(n, F).normal_()
         measure(f"computers fanout={fanout}", blk, n, e, x, blk.col)
         del x
     del loader, b

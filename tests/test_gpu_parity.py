@@ -108,38 +108,6 @@ def test_agg_fwd_long_rows_and_determinism(dev):
     assert rel_err(a, want) < max(RTOL, 4 * err_ref), (rel_err(a, want), err_ref)
 
 
-@pytest.mark.parametrize("variant", [104, 106, 113, 114, 204, 206, 213, 214])
-@pytest.mark.parametrize("F", [4, 64, 100, 128])
-def test_agg_fwd_smem_staged_variants_bitwise_equal(dev, variant, F):
-    """k_agg_fwd_bulk (rows staged through shared memory by UBLKCP / LDGSTS, ngnn_set_tuning(5, v)) against the oracle
-    and, bit for bit, against the register-pipelined kernel: rows of degree 0, 1..25, 40 and 700 (several units per row,
-    several index windows), prefix trimming, fused root gather."""
-    from noise_gnn_b200 import _lib, ops
-    n = 3000
-    g = torch.Generator().manual_seed(F + variant)
-    deg = torch.randint(0, 26, (n,), generator=g)
-    deg[7], deg[8], deg[9], deg[2999] = 0, 40, 700, 33
-    dst = torch.repeat_interleave(torch.arange(n), deg)
-    src = torch.randint(0, n, (dst.numel(),), generator=g)
-    ei = torch.stack([src, dst])
-    x = torch.randn(n, F, generator=g)
-    want = sage_oracle.mean_aggregate(x.double(), ei)
-    blk = ops.coo_to_csr(ei.to(dev), n)
-    root_idx = torch.randint(0, n, (n,), generator=g, dtype=torch.int32)
-    base, base_root = ops.agg_fwd(blk.rowptr, blk.col, x.to(dev), n, root_idx=root_idx.to(dev))
-    _lib.call("ngnn_set_tuning", 5, variant)
-    try:
-        got, got_root = ops.agg_fwd(blk.rowptr, blk.col, x.to(dev), n, root_idx=root_idx.to(dev))
-        plain = ops.agg_fwd(blk.rowptr, blk.col, x.to(dev), n)
-        part = ops.agg_fwd(blk.rowptr, blk.col, x.to(dev), 1234)
-    finally:
-        _lib.call("ngnn_set_tuning", 5, 0)
-    assert rel_err(got, want) < RTOL
-    assert torch.equal(got, base) and torch.equal(plain, base) and torch.equal(part, base[:1234])
-    assert torch.equal(got_root, base_root) and torch.equal(got_root.cpu(), x[root_idx.long()])
-    assert float(got[7].abs().max()) == 0.0
-
-
 @pytest.mark.parametrize("F", [64, 100, 256, 47])
 def test_agg_bwd_matches_oracle(dev, F):
     from noise_gnn_b200 import ops
