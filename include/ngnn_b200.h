@@ -344,6 +344,26 @@ int32_t ngnn_ct_loss(const float* logits1, int64_t ld1, const float* logits2, in
                      int64_t num_remember, float* stats /*[6]*/, float* dlogits1, int64_t ldd1, float* dlogits2,
                      int64_t ldd2, int32_t* order1, int32_t* order2, float* scratch, ngnn_stream_t stream);
 
+/* ---- SAGEPL extras (reference src/models/layers/sagePL.py:41-49, src/utils/augmentation.py:88-102) ----
+ * adding_noise, fused: out[i,:] = x[i,:] + s_i * rate * v_i / max(|v_i|_2, 1e-12),  v_i = noise[idx[i],:]
+ *   idx = the block's n_id (reference line 47: s_i = 1) or NULL = identity with use_sign (line 44: s_i = sign(x[i,:])).
+ * Backward w.r.t. the noise table: dnoise[idx[i],:] += rate/|v_i| * (g - u_i (u_i . g)),  g = s_i * dout[i,:], u_i = v_i/|v_i|
+ *   (added with atomics: a block's n_id are distinct, so every address is touched once and the result is deterministic;
+ *   the caller zeroes dnoise).  The gradient w.r.t. x is dout itself.                                               */
+int32_t ngnn_noise_add_fwd(const float* x, int64_t ld_x, const float* noise, int64_t ld_noise, const int32_t* idx,
+                           int64_t n, int64_t F, float rate, int32_t use_sign, float* out, int64_t ld_out,
+                           ngnn_stream_t stream);
+int32_t ngnn_noise_add_bwd(const float* dout, int64_t ld_d, const float* x, int64_t ld_x, const float* noise,
+                           int64_t ld_noise, const int32_t* idx, int64_t n, int64_t F, float rate, int32_t use_sign,
+                           float* dnoise, int64_t ld_dn, ngnn_stream_t stream);
+/* shuffle_pos: out = x with, per row, k distinct random positions' values permuted among themselves
+ *   pos = Robert Floyd subset of [0,F) (insertion order), sel = Fisher-Yates shuffle of pos, out[row,pos[j]] = x[row,sel[j]].
+ * Philox4x32-10 keyed (seed) with counter (row, draw/4, offset): bit-exact target oracle/sagepl_oracle.py::shuffle_rows.
+ * The reference draws from torch.randperm, so only the LAW is comparable (validity: each row is a permutation of itself
+ * that moves at most k positions).  F <= 2048; x and out must not alias.                                            */
+int32_t ngnn_shuffle_rows(const float* x, int64_t ld_x, int64_t n, int64_t F, int32_t k, uint64_t seed, uint64_t offset,
+                          float* out, int64_t ld_out, ngnn_stream_t stream);
+
 /* 1 (default): inside ngnn_sage_step the weight gradients of layers >= 2 run on an internal auxiliary stream, forked
  * from / joined back into the caller's stream with events (they are off the backward's critical path); 0: strictly
  * one stream.                                                                                                  */

@@ -7,6 +7,8 @@ underscore.)  Public surface, mirroring the two third-party entry points the ref
 * ``NeighborLoader``  drop-in for ``torch_geometric.loader.NeighborLoader``  (reference src/pipeline.py:6,75-92,152)
 * ``Data``            minimal ``torch_geometric.data.Data`` bag
 * ``SAGE``            the reference's network module (src/models/layers/sage.py:6-78) with a trimmed fused mode
+* ``SAGEPL`` / ``shuffle_pos``  the noise-injecting SAGE variant (src/models/layers/sagePL.py) and the feature-shuffling
+                      augmentation (src/utils/augmentation.py:88-102): fused gather-normalize-add kernel, device-side shuffle
 * ``GCNConv`` / ``SimpleGCN``  the reference's ``module: 'gcn'`` path (src/models/layers/convolution.py:7-53,
                       ``GCNConv(normalize=False)``): same kernels, sum instead of mean, linear before aggregation
 * ``ops``             tensor-level wrappers over the C ABI in include/ngnn_b200.h (libngnn_b200.so)
@@ -36,13 +38,16 @@ def __getattr__(name):
     if name == "SAGE":
         from .sage import SAGE
         return SAGE
+    if name in ("SAGEPL", "shuffle_pos"):
+        from . import sagepl
+        return getattr(sagepl, name)
     if name == "CTLoss":
         from .losses import CTLoss
         return CTLoss
-    if name in ("ops", "conv", "loader", "sage", "gcn", "losses", "synthetic", "train", "dp"):
+    if name in ("ops", "conv", "loader", "sage", "sagepl", "gcn", "losses", "synthetic", "train", "dp"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)
 
 
-__all__ = ["SAGEConv", "GCNConv", "NeighborLoader", "Data", "Batch", "SAGE", "SimpleGCN", "CTLoss", "build"]
+__all__ = ["SAGEConv", "GCNConv", "NeighborLoader", "Data", "Batch", "SAGE", "SAGEPL", "shuffle_pos", "SimpleGCN", "CTLoss", "build"]

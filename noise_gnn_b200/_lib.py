@@ -55,6 +55,9 @@ SIGNATURES = {
     "ngnn_sage_backward": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_size_t, _P]),
     "ngnn_ct_loss": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P,
                                c_int64, _P, _P, _P, _P]),
+    "ngnn_noise_add_fwd": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_float, c_int32, _P, c_int64, _P]),
+    "ngnn_noise_add_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_float, c_int32, _P, c_int64, _P]),
+    "ngnn_shuffle_rows": (c_int32, [_P, c_int64, c_int64, c_int64, c_int32, c_uint64, c_uint64, _P, c_int64, _P]),
     "ngnn_set_step_overlap": (c_int32, [c_int32]),
     "ngnn_probe_enable": (c_int32, [c_int32]),
     "ngnn_probe_read": (c_int32, [_P, c_int32, _P]),

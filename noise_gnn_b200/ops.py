@@ -357,6 +357,44 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr=1e-3, betas=(0.9, 0
                   int(advance_step), _stream())
 
 
+# ----------------------------------------------------------------------------- SAGEPL extras
+class NoiseAddFunction(torch.autograd.Function):
+    """noisy_x = x + s * rate * normalize(noise[idx]) (reference sagePL.py:41-49), one fused pass each way."""
+
+    @staticmethod
+    def forward(ctx, x, noise, idx, rate: float, use_sign: bool):
+        x, noise = _rows(x, "x"), _rows(noise, "noise")
+        n, F_ = x.shape
+        out = torch.empty((n, F_), dtype=_F32, device=x.device)
+        _lib.call("ngnn_noise_add_fwd", _ptr(x), _ld(x), _ptr(noise), _ld(noise), _ptr(idx), n, F_, float(rate), int(use_sign),
+                  _ptr(out), _ld(out), _stream())
+        ctx.save_for_backward(x if use_sign else None, noise, idx)
+        ctx.rate, ctx.use_sign = float(rate), bool(use_sign)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, noise, idx = ctx.saved_tensors
+        dout = _rows(dout, "dout")
+        n, F_ = dout.shape
+        dnoise = None
+        if ctx.needs_input_grad[1]:
+            dnoise = torch.zeros_like(noise)           # dense, like the reference's index_select backward
+            _lib.call("ngnn_noise_add_bwd", _ptr(dout), _ld(dout), _ptr(x), _ld(x) if x is not None else 0, _ptr(noise), _ld(noise),
+                      _ptr(idx), n, F_, ctx.rate, int(ctx.use_sign), _ptr(dnoise), _ld(dnoise), _stream())
+        return (dout if ctx.needs_input_grad[0] else None), dnoise, None, None, None
+
+
+def shuffle_rows(x: torch.Tensor, k: int, seed: int = 1232, offset: int = 0) -> torch.Tensor:
+    """Per row, k distinct random positions get their values permuted among themselves (shuffle_pos on the device)."""
+    _check_cuda(x)
+    x = _rows(x, "x")
+    out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    _lib.call("ngnn_shuffle_rows", _ptr(x), _ld(x), x.size(0), x.size(1), int(k), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1),
+              _ptr(out), _ld(out), _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- SAGEConv autograd
 class SAGEConvFunction(torch.autograd.Function):
     """out[:n_dst] = lin_l(mean_{j->i} x_j) + lin_r(x_i), on a CSR block; backward is atomic-free."""

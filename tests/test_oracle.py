@@ -183,3 +183,32 @@ def test_ctloss_autograd_nodes_are_independent():
     l1.backward()
     (l2 * 2).backward()
     assert torch.equal(y1.grad, d1) and torch.equal(y2.grad, d2 * 2) and float(l1) == 1.5
+
+
+def test_shuffle_rows_twin_follows_the_reference_law():
+    """oracle/sagepl_oracle.shuffle_rows (the bit-exact target of ngnn_shuffle_rows): per row, at most k = int(F * prob)
+    positions change and the row stays a permutation of itself (reference src/utils/augmentation.py:88-102)."""
+    import numpy as np
+    from oracle import sagepl_oracle
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((40, 100)).astype(np.float32)
+    for k in (0, 1, 10, 50, 100):
+        out = sagepl_oracle.shuffle_rows(x, k, seed=1232, offset=3)
+        assert np.array_equal(np.sort(out, 1), np.sort(x, 1))
+        assert int((out != x).sum(1).max()) <= k
+    a = sagepl_oracle.shuffle_rows(x, 10, seed=1232, offset=3)
+    assert np.array_equal(a, sagepl_oracle.shuffle_rows(x, 10, seed=1232, offset=3))
+    assert not np.array_equal(a, sagepl_oracle.shuffle_rows(x, 10, seed=1232, offset=4))
+    assert 5 < (a != x).sum(1).mean() <= 10          # ~k(1 - 1/k) positions actually move
+
+
+def test_adding_noise_oracle_matches_the_reference_expression():
+    import torch
+    from oracle import sagepl_oracle
+    x, noise = torch.randn(6, 5), torch.randn(9, 5)
+    n_id = torch.tensor([8, 0, 3, 4, 1, 2])
+    want = x + torch.nn.functional.normalize(noise[n_id]) * 0.1
+    assert torch.allclose(sagepl_oracle.adding_noise(x, noise, 0.1, n_id), want)
+    x9 = torch.randn(9, 5)
+    want = x9 + torch.sign(x9) * torch.nn.functional.normalize(noise) * 0.1
+    assert torch.allclose(sagepl_oracle.adding_noise(x9, noise, 0.1, None), want)
