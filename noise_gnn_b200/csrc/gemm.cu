@@ -158,9 +158,10 @@ int32_t wgrad_impl(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_
   const size_t part_bytes = ws_bytes - 256 - colsum_ws_bytes(n, O);
 
   // dW[o,f] = sum_i dy[i,o] * a[i,f] : A(m=o,k=i) = dy[i*ld+o], B(n=f,k=i) = a[i*ld+f]
-  bool done = false;
+  bool done = false, db_done = false;
   if (!g_force_simt && F > 0 && (dw_l || dw_r)) {
-    int32_t rc = tc_gemm_wgrad(dy, ld_dy, a_l, ld_al, a_r, ld_ar, n, n_dev, F, O, dw_l, dw_r, accumulate, part, part_bytes, st);
+    int32_t rc = tc_gemm_wgrad(dy, ld_dy, a_l, ld_al, a_r, ld_ar, n, n_dev, F, O, dw_l, dw_r, db, &db_done, accumulate, part,
+                               part_bytes, st);
     if (rc == NGNN_OK) done = true;
     else if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
@@ -188,7 +189,7 @@ int32_t wgrad_impl(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_
       }
     }
   }
-  if (db) {
+  if (db && !db_done) {
     const int32_t Cs = colsum_slices(n, O);
     dim3 grid((unsigned)ceil_div(O, 32), (unsigned)Cs);
     k_colsum_partial<<<grid, 256, 0, st>>>(dy, ld_dy, Ext{n_dev, n}, O, cpart);

@@ -185,25 +185,31 @@ __global__ void k_reduce_partials(const float* __restrict__ part, int64_t stride
   out[i] = accumulate ? out[i] + s : s;
 }
 
-// Two independent partial sets reduced by one launch (blockIdx.y selects): dW_l and dW_r of one K-WGRAD call.
-__global__ void k_reduce_partials2(const float* __restrict__ part0, const float* __restrict__ part1, int64_t stride,
-                                   int32_t splits, int64_t n, float* __restrict__ out0, float* __restrict__ out1,
-                                   int32_t accumulate) {
-  const float* part = blockIdx.y == 0 ? part0 : part1;
-  float* out = blockIdx.y == 0 ? out0 : out1;
+// Up to three independent partial sets reduced by one launch (blockIdx.y selects): dW_l, dW_r and db of one K-WGRAD call.
+struct ReduceJob {
+  const float* part;     // [splits][stride]
+  float* out;            // [n]
+  int64_t n, stride;
+};
+struct ReduceJobs {
+  ReduceJob job[3];
+  int32_t n;
+};
+__global__ void k_reduce_partials_multi(const ReduceJobs jobs, int32_t splits, int32_t accumulate) {
+  const ReduceJob jb = jobs.job[blockIdx.y];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= jb.n) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int32_t z = 0;
   for (; z + 3 < splits; z += 4) {
-    s0 += part[(int64_t)z * stride + i];
-    s1 += part[(int64_t)(z + 1) * stride + i];
-    s2 += part[(int64_t)(z + 2) * stride + i];
-    s3 += part[(int64_t)(z + 3) * stride + i];
+    s0 += jb.part[(int64_t)z * jb.stride + i];
+    s1 += jb.part[(int64_t)(z + 1) * jb.stride + i];
+    s2 += jb.part[(int64_t)(z + 2) * jb.stride + i];
+    s3 += jb.part[(int64_t)(z + 3) * jb.stride + i];
   }
-  for (; z < splits; ++z) s0 += part[(int64_t)z * stride + i];
+  for (; z < splits; ++z) s0 += jb.part[(int64_t)z * jb.stride + i];
   const float s = (s0 + s1) + (s2 + s3);
-  out[i] = accumulate ? out[i] + s : s;
+  jb.out[i] = accumulate ? jb.out[i] + s : s;
 }
 
 // column sums of dy over a row slice: part[z*O + o] = sum_{i in slice z} dy[i*ld + o].

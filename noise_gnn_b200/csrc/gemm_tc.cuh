@@ -879,6 +879,7 @@ struct TcWgradParams {
   int32_t tiles_per_seg;
   int32_t n;                  // reduction rows (capacity when n_dev != nullptr)
   const int32_t* n_dev;       // optional device-side reduction length (clamped to n)
+  float* db_part;             // optional [splits][O]: column sums of dY over this CTA's slice (bias gradient), TS form only
   TcWgradSeg seg[2];
 };
 
@@ -992,6 +993,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
   } else if (warp < 6) {
     // ===================== converter warps (2..5): hi / lo split of both operands, rows >= n zeroed =====================
     const int t = threadIdx.x - 64;
+    float db_acc = 0.f;                                         // TS: this thread's output row o, summed over the slice (bias gradient)
     StageIter si{0, 0u, p.stages};
     for (int32_t it = 0; it < KB; ++it, si.next()) {
       const int s = si.s;
@@ -1014,6 +1016,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
             const int i = half * 16 + ii;
             float x = box[i * 32 + ((((lane >> 3) ^ (i & 3)) << 3) | (lane & 7))];
             if (i >= rows_ok) x = 0.f;
+            db_acc += x;
             float hx, lx;
             split_tf32(x, hx, lx);
             h[ii] = __float_as_uint(hx); l[ii] = __float_as_uint(lx);
@@ -1052,6 +1055,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
       }
       fence_proxy_async_smem();
       mbar_arrive(&full_conv[s]);
+    }
+    // bias gradient: db_part[slice][o] = sum over this slice's rows of dY[i, o]  (one CTA per (o tile, slice) writes it)
+    if (TS && p.db_part != nullptr && blockIdx.y == 0) {
+      const int32_t o = o0 + (warp & 3) * 32 + lane;
+      if (o < p.O) p.db_part[(int64_t)blockIdx.z * p.O + o] = db_acc;
     }
   } else {
     // ===================== promoter / epilogue warps (6..13) =====================
@@ -1133,14 +1141,17 @@ static inline size_t tc_wgrad_ws_bytes(int64_t n, int64_t F, int64_t O) {
   const TcWgradPlan pl = tc_wgrad_plan(n, F, O, 2);
   const TcWgradPlan pl1 = tc_wgrad_plan(n, F, O, 1);
   const int64_t s = pl.splits > pl1.splits ? pl.splits : pl1.splits;
-  return 2 * align_up((size_t)s * O * F * sizeof(float), 256) + 256;
+  return 2 * align_up((size_t)s * O * F * sizeof(float), 256) + align_up((size_t)s * O * sizeof(float), 256) + 256;
 }
 
 // dw_l (+)= dy^T a_l ; dw_r (+)= dy^T a_r.  UNSUPPORTED when an operand is not TMA-addressable.
 // n_dev (optional): device-side reduction length, n is then the capacity the launch is sized for.
+// db (optional): the bias gradient, column sums of dy, folded into the same pass over dy (TS form); *db_done says whether it was.
 static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_al, const float* a_r,
                                     int64_t ld_ar, int64_t n, const int32_t* n_dev, int64_t F, int64_t O, float* dw_l,
-                                    float* dw_r, int32_t accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+                                    float* dw_r, float* db, bool* db_done, int32_t accumulate, void* ws, size_t ws_bytes,
+                                    cudaStream_t st) {
+  if (db_done) *db_done = false;
   if (n < 1 || F < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
   if (!tma_addressable(dy, ld_dy)) return NGNN_E_UNSUPPORTED;
   if (dw_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
@@ -1161,10 +1172,12 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
 
   float* part0 = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
   float* part1 = part0 + align_up((size_t)pl.splits * O * F * sizeof(float), 256) / sizeof(float);
-  const bool direct = pl.splits == 1 && !accumulate;
+  float* part_db = part1 + align_up((size_t)pl.splits * O * F * sizeof(float), 256) / sizeof(float);
+  const bool fuse_db = db != nullptr && pl.ts;
+  const bool direct = pl.splits == 1 && !accumulate && !fuse_db;
   TcWgradParams p{};
   p.O = (int32_t)O; p.BN = pl.BN; p.nbox = pl.nbox; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
-  p.n = (int32_t)n; p.n_dev = n_dev;
+  p.n = (int32_t)n; p.n_dev = n_dev; p.db_part = fuse_db ? part_db : nullptr;
   int ns = 0;
   float* outs[2] = {nullptr, nullptr};
   float* parts[2] = {nullptr, nullptr};
@@ -1182,10 +1195,14 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
   else k_tc_wgrad<false><<<grid, TW_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
   NGNN_LAUNCH_CHECK();
   if (!direct) {
-    // same per-element summation order as k_reduce_partials; both weight gradients in one launch
-    dim3 rgrid((unsigned)ceil_div(O * F, 256), (unsigned)ns);
-    k_reduce_partials2<<<rgrid, 256, 0, st>>>(parts[0], parts[ns - 1], O * F, pl.splits, O * F, outs[0], outs[ns - 1], accumulate);
+    // same per-element summation order as k_reduce_partials; both weight gradients and the bias gradient in one launch
+    ReduceJobs jobs{};
+    for (int j = 0; j < ns; ++j) jobs.job[jobs.n++] = ReduceJob{parts[j], outs[j], O * F, O * F};
+    if (fuse_db) jobs.job[jobs.n++] = ReduceJob{part_db, db, O, O};
+    dim3 rgrid((unsigned)ceil_div(O * F, 256), (unsigned)jobs.n);
+    k_reduce_partials_multi<<<rgrid, 256, 0, st>>>(jobs, pl.splits, accumulate);
     NGNN_LAUNCH_CHECK();
+    if (fuse_db && db_done) *db_done = true;
   }
   return NGNN_OK;
 }

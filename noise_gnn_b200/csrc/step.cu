@@ -277,15 +277,6 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
       rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
                       grads + lp.off_wl, grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes,
                       aux->stream);
-    } else if (use_aux) {      // layer 1 closes the step: its bias gradient (column sums of dY) runs beside the tensor-core kernel
-      NGNN_CUDA(cudaEventRecord(aux->fork, st));
-      NGNN_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-      aux_used = true;
-      rc = wgrad_impl(F32(lp.dy), lp.ldo, nullptr, 0, nullptr, 0, n_rows.cap, n_rows.dev, lp.F, lp.O, nullptr, nullptr,
-                      grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes, aux->stream);
-      if (rc != NGNN_OK) return rc;
-      rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
-                      grads + lp.off_wl, grads + lp.off_wr, nullptr, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, st);
     } else {
       rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
                       grads + lp.off_wl, grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, st);
