@@ -74,6 +74,7 @@ struct StepCtl {
 // Library-internal entry points of the dense kernels (gemm.cu) for the fused step (step.cu): the split weight planes
 // are prepared once per step, off the critical path, instead of inside every GEMM call.
 //   mode 0: forward pack [W_l | W_r] (K-major) -> ws of ngnn_sage_gemm_workspace_bytes(F, O)
+//   mode 2: the same without padding between the halves (the two activations are the halves of one [n, 2F] matrix)
 //   mode 1: data-gradient pack [W_l^T ; W_r^T]  -> ws of ngnn_sage_dgrad_workspace_bytes(F, O)
 // Returns NGNN_E_UNSUPPORTED when the shape takes the SIMT kernels (which read the weights directly).
 // K-AGG forward from the resident feature table with a hot-row split (agg.cu): table rows < hot_rows are gathered with
@@ -95,7 +96,7 @@ int32_t prep_batch_launch(cudaStream_t st);
 int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l, const float* w_r,
                       const float* bias, int64_t n, int64_t F, int64_t O, int32_t act, float drop_p, uint64_t seed,
                       uint64_t offset, float* out, int64_t ld_out, int32_t* path, void* ws, size_t ws_bytes, cudaStream_t st,
-                      bool prepped, const int32_t* n_dev, const struct StepCtl* ctl, uint32_t ctl_layer);
+                      bool prepped, const int32_t* n_dev, const struct StepCtl* ctl, uint32_t ctl_layer, bool concat_k);
 int32_t dgrad_impl(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr, int64_t n,
                    int64_t F, int64_t O, float* dmean_scaled, int64_t ld_dmean, float* dx_root, int64_t ld_root, void* ws,
                    size_t ws_bytes, cudaStream_t st, bool prepped, const int32_t* n_dev);

@@ -50,7 +50,7 @@ int32_t prep_batch_add(int32_t mode, const float* w_l, const float* w_r, int64_t
   PrepBatch& b = t_prep_batch;
   if (b.n_jobs >= PREP_MAX_JOBS) return NGNN_E_UNSUPPORTED;
   PrepParams pp{};
-  const int32_t rc = mode == 0 ? tc_prep_fwd(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, nullptr, &pp)
+  const int32_t rc = mode != 1 ? tc_prep_fwd(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, nullptr, &pp, mode == 2)
                                : tc_prep_dgrad(w_l, w_r, w_l != nullptr, w_r != nullptr, F, O, ws, ws_bytes, nullptr, &pp);
   if (rc != NGNN_OK) return rc;
   b.job[b.n_jobs] = pp;
@@ -70,7 +70,7 @@ int32_t prep_batch_launch(cudaStream_t st) {
 int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t ld_ar, const float* w_l, const float* w_r,
                       const float* bias, int64_t n, int64_t F, int64_t O, int32_t act, float drop_p, uint64_t seed,
                       uint64_t offset, float* out, int64_t ld_out, int32_t* path, void* ws, size_t ws_bytes, cudaStream_t st,
-                      bool prepped, const int32_t* n_dev, const StepCtl* ctl, uint32_t ctl_layer) {
+                      bool prepped, const int32_t* n_dev, const StepCtl* ctl, uint32_t ctl_layer, bool concat_k) {
   NGNN_REQUIRE(n >= 0 && F >= 0 && O >= 0, NGNN_E_INVALID, "gemm_fwd: negative size");
   NGNN_REQUIRE(act == NGNN_ACT_NONE || act == NGNN_ACT_RELU, NGNN_E_INVALID, "gemm_fwd: unknown activation %d", act);
   NGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, NGNN_E_INVALID, "gemm_fwd: dropout p=%f outside [0,1)", (double)drop_p);
@@ -84,11 +84,11 @@ int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t
 
   if (!g_force_simt) {
     int32_t rc = tc_gemm_fwd(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out,
-                             ws, ws_bytes, st, prepped, n_dev, ctl, ctl_layer);
+                             ws, ws_bytes, st, prepped, n_dev, ctl, ctl_layer, concat_k);
     if (rc == NGNN_OK) { if (path) *path = 1; return NGNN_OK; }
     if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
-  NGNN_REQUIRE(n_dev == nullptr && ctl == nullptr, NGNN_E_UNSUPPORTED,
+  NGNN_REQUIRE(n_dev == nullptr && ctl == nullptr && !concat_k, NGNN_E_UNSUPPORTED,
                "gemm_fwd: device-side extents need TMA-addressable operands (16-byte aligned bases, ld %% 4 == 0)");
 
   SimtGemmParams p{};
@@ -211,7 +211,7 @@ int32_t ngnn_sage_gemm_fwd(const float* a_l, int64_t ld_al, const float* a_r, in
                            float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, int32_t* path,
                            void* ws, size_t ws_bytes, ngnn_stream_t stream) {
   return gemm_fwd_impl(a_l, ld_al, a_r, ld_ar, w_l, w_r, bias, n, F, O, act, drop_p, seed, offset, out, ld_out, path, ws,
-                       ws_bytes, as_stream(stream), false, nullptr, nullptr, 0);
+                       ws_bytes, as_stream(stream), false, nullptr, nullptr, 0, false);
 }
 
 int32_t ngnn_sage_dgrad(const float* dy, int64_t ld_dy, const float* w_l, const float* w_r, const int32_t* rowptr,

@@ -199,17 +199,18 @@ __global__ void k_reduce_partials_multi(const ReduceJobs jobs, int32_t splits, i
   const ReduceJob jb = jobs.job[blockIdx.y];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= jb.n) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  // eight independent chains: the loads of a slice round are all in flight together (the kernel is pure latency)
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int32_t z = 0;
-  for (; z + 3 < splits; z += 4) {
-    s0 += jb.part[(int64_t)z * jb.stride + i];
-    s1 += jb.part[(int64_t)(z + 1) * jb.stride + i];
-    s2 += jb.part[(int64_t)(z + 2) * jb.stride + i];
-    s3 += jb.part[(int64_t)(z + 3) * jb.stride + i];
+  for (; z + 7 < splits; z += 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] += __ldg(jb.part + (int64_t)(z + q) * jb.stride + i);
   }
-  for (; z < splits; ++z) s0 += jb.part[(int64_t)z * jb.stride + i];
-  const float s = (s0 + s1) + (s2 + s3);
-  jb.out[i] = accumulate ? jb.out[i] + s : s;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (z + q < splits) s[q] += __ldg(jb.part + (int64_t)(z + q) * jb.stride + i);
+  const float t = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  jb.out[i] = accumulate ? jb.out[i] + t : t;
 }
 
 // column sums of dy over a row slice: part[z*O + o] = sum_{i in slice z} dy[i*ld + o].

@@ -360,7 +360,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(bias_s + 288);
   uint64_t* full_conv = full_raw + TC_MAX_STAGES;
   uint64_t* empty = full_conv + TC_MAX_STAGES;
-  uint64_t* tmem_full = empty + TC_MAX_STAGES;      // [2]
+  uint64_t* a_free = empty + TC_MAX_STAGES;         // TS: the converters have read the raw A tile out of the stage
+  uint64_t* tmem_full = a_free + TC_MAX_STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -381,7 +382,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
     tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
     // full_raw: the raw A tile landed (converters wait); full_conv: 128 converter arrivals + the producer's arrival
     // carrying the B tiles' bytes (the MMA thread waits on this one only)
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 129); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 129); mbar_init(&empty[s], 1); mbar_init(&a_free[s], 128);
+    }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * TG_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -411,15 +414,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
         for (int32_t kb = 0; kb < KB; ++kb, ++it, si.next()) {
           const int s = si.s;
           const uint32_t ph = si.ph;
-          mbar_wait(&empty[s], ph ^ 1u);
-          if (tr && it < 32) tr[8 + it * 8 + 0] = clock64();
           uint8_t* st = smem + (size_t)s * stage_bytes;
-          mbar_arrive_expect_tx(&full_raw[s], a_bytes);
-          mbar_arrive_expect_tx(&full_conv[s], 2 * b_bytes);
           const bool first = kb < p.kblocks1;
           const int32_t ka = (first ? kb : kb - p.kblocks1) * TC_BK;
           const int32_t kbk = first ? ka : p.b_koff2 + ka;
+          // TS: the raw A slot is free as soon as the converters have copied it to registers — about one MMA period before
+          // the stage's MMAs retire — so the A tile (the one with a conversion step behind it) is requested that much earlier:
+          // the loop TMA latency + conversion + MMA no longer has to fit into `stages` MMA periods.
+          if (TS) mbar_wait(&a_free[s], ph ^ 1u); else mbar_wait(&empty[s], ph ^ 1u);
+          if (tr && it < 32) tr[8 + it * 8 + 0] = clock64();
+          mbar_arrive_expect_tx(&full_raw[s], a_bytes);
           tma_load_2d(st, first ? &tmA1 : &tmA2, &full_raw[s], ka, m0);
+          if (TS) mbar_wait(&empty[s], ph ^ 1u);       // B tiles (and the stage's TMEM A columns) are in use until the MMAs retire
+          mbar_arrive_expect_tx(&full_conv[s], 2 * b_bytes);
           tma_load_2d(st + a_span, &tmBhi, &full_conv[s], kbk, b_row);
           tma_load_2d(st + a_span + b_bytes, &tmBlo, &full_conv[s], kbk, b_row);
         }
@@ -478,17 +485,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
         mbar_wait(&full_raw[s], ph);
         if (tr && t == 0 && it < 32) tr[8 + it * 8 + 1] = clock64();
         if (TS) {
-          // thread = one tile row (TMEM lane 32*(warp%4) + lane): its 128 swizzled bytes -> hi / lo -> tensor memory
+          // thread = one tile row (TMEM lane 32*(warp%4) + lane): its 128 swizzled bytes -> registers (the shared-memory slot
+          // is handed back at once) -> hi / lo -> tensor memory (once the MMAs of the stage's previous use have retired)
           const int r = (warp & 3) * 32 + lane;
           const uint8_t* rowp = smem + (size_t)s * stage_bytes + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
           const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tmem_a0 + (uint32_t)s * TS_A_COLS;
+          float4 raw[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)                      // 16-byte chunk j of the row sits at chunk position j ^ (r % 8)
+            raw[j] = *reinterpret_cast<const float4*>(rowp + ((j ^ (r & 7)) << 4));
+          mbar_arrive(&a_free[s]);
+          mbar_wait(&empty[s], ph ^ 1u);
+          tc_fence_after();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t h[16], l[16];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              const int j = half * 4 + jj;             // 16-byte chunk j of the row sits at chunk position j ^ (r % 8)
-              const float4 x = *reinterpret_cast<const float4*>(rowp + ((j ^ (r & 7)) << 4));
+              const float4 x = raw[half * 4 + jj];
               float hx, lx;
               split_tf32(x.x, hx, lx); h[4 * jj + 0] = __float_as_uint(hx); l[4 * jj + 0] = __float_as_uint(lx);
               split_tf32(x.y, hx, lx); h[4 * jj + 1] = __float_as_uint(hx); l[4 * jj + 1] = __float_as_uint(lx);
@@ -706,11 +720,14 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
 // drifts past the 1e-5 bar (see the K-WGRAD notes below): wider contractions take the SIMT kernel.
 constexpr int TC_MAX_CHAIN_KBLOCKS = 40;
 
+// concat_k: the two operands are the halves of ONE [n, 2F] matrix ([mean | root] side by side, layer 1 of the fused step), so the
+// weights are packed [W_l | W_r] without padding in between and the contraction runs over ceil(2F / 32) K-blocks instead of
+// 2 * ceil(F / 32) (F = 100: 7 instead of 8).
 static inline int32_t tc_prep_fwd(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
-                                  size_t ws_bytes, cudaStream_t st, PrepParams* collect = nullptr) {
+                                  size_t ws_bytes, cudaStream_t st, PrepParams* collect = nullptr, bool concat_k = false) {
   if (F < 1 || O < 1 || 2 * ceil_div(F, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_fwd_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
-  const int32_t Fpad = round_up_i(F, TC_BK), Kpack = 2 * Fpad;
+  const int32_t Fpad = concat_k ? (int32_t)F : round_up_i(F, TC_BK), Kpack = concat_k ? round_up_i(2 * F, TC_BK) : 2 * Fpad;
   float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
   float* lo = hi + align_up((size_t)O * Kpack * sizeof(float), 256) / sizeof(float);
   PrepParams pp{};
@@ -727,19 +744,20 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
                                   const float* w_r, const float* bias, int64_t n, int64_t F, int64_t O, int32_t act,
                                   float drop_p, uint64_t seed, uint64_t offset, float* out, int64_t ld_out, void* ws,
                                   size_t ws_bytes, cudaStream_t st, bool prepped = false, const int32_t* n_dev = nullptr,
-                                  const StepCtl* ctl = nullptr, uint32_t ctl_layer = 0) {
+                                  const StepCtl* ctl = nullptr, uint32_t ctl_layer = 0, bool concat_k = false) {
   if (F < 1 || n < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
+  if (concat_k && !(a_l && a_r && a_r == a_l + F && ld_al == ld_ar && ld_al >= 2 * F)) return NGNN_E_UNSUPPORTED;
   if (2 * ceil_div(F, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
   if (a_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
   if (a_r && !tma_addressable(a_r, ld_ar)) return NGNN_E_UNSUPPORTED;
   if (!a_l && !a_r) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_fwd_ws_bytes(F, O) || get_encode_fn() == nullptr) return NGNN_E_UNSUPPORTED;
 
-  const int32_t Fpad = round_up_i(F, TC_BK), Kpack = 2 * Fpad;
+  const int32_t Fpad = concat_k ? (int32_t)F : round_up_i(F, TC_BK), Kpack = concat_k ? round_up_i(2 * F, TC_BK) : 2 * Fpad;
   float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
   float* lo = hi + align_up((size_t)O * Kpack * sizeof(float), 256) / sizeof(float);
   if (!prepped) {
-    const int32_t rc = tc_prep_fwd(w_l, w_r, a_l != nullptr, a_r != nullptr, F, O, ws, ws_bytes, st);
+    const int32_t rc = tc_prep_fwd(w_l, w_r, a_l != nullptr, a_r != nullptr, F, O, ws, ws_bytes, st, nullptr, concat_k);
     if (rc != NGNN_OK) return rc;
   }
 
@@ -747,8 +765,8 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
   CUtensorMap tA1, tA2, tBh, tBl;
   const float* a1 = a_l ? a_l : a_r;
   const int64_t ld1 = a_l ? ld_al : ld_ar;
-  const bool two = a_l && a_r;
-  bool ok = make_tmap_2d(&tA1, a1, n, F, ld1, TC_BM);
+  const bool two = a_l && a_r && !concat_k;
+  bool ok = make_tmap_2d(&tA1, a1, n, concat_k ? 2 * F : F, ld1, TC_BM);
   ok = ok && make_tmap_2d(&tA2, two ? a_r : a1, n, F, two ? ld_ar : ld1, TC_BM);
   ok = ok && make_tmap_2d(&tBh, hi, O, Kpack, Kpack, (uint32_t)pl.BN);
   ok = ok && make_tmap_2d(&tBl, lo, O, Kpack, Kpack, (uint32_t)pl.BN);
@@ -757,7 +775,7 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
   TcGemmParams p{};
   p.M = (int32_t)n; p.M_dev = n_dev; p.ctl = ctl; p.ctl_layer = ctl_layer;
   p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
-  p.kblocks1 = Fpad / TC_BK; p.kblocks2 = two ? Fpad / TC_BK : 0;
+  p.kblocks1 = concat_k ? Kpack / TC_BK : Fpad / TC_BK; p.kblocks2 = two ? Fpad / TC_BK : 0;
   p.b_koff2 = Fpad;
   if (!a_l) { p.b_koff2 = 0; /* single operand is a_r: its weights sit in segment 1 of the pack */ }
   p.seg[0] = TcSegment{out, ld_out, (int32_t)O, 0, 0};
@@ -928,7 +946,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmX2);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], 128); mbar_init(&empty[s], 1); }
+    // full_conv: TS = 128 A-converter + 256 B-converter (promoter warps) arrivals; SS = the 128 converter threads do both
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_conv[s], TS ? 128 + 32 * TW_EPI_WARPS : 128); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 32 * TW_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -1024,18 +1043,6 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
           tmem_st16(ta + half * 16, h);
           tmem_st16(ta + 32 + half * 16, l);
         }
-        // B: split in place (hi) + lo plane; float4 q of a box belongs to reduction row (q % 256) / 8
-        float4* bh = reinterpret_cast<float4*>(st + a_span);
-        float4* bl = reinterpret_cast<float4*>(st + a_span + b_bytes);
-        const int b4 = (int)(b_bytes / 16);
-        for (int i = t; i < b4; i += 128) {
-          float4 x = bh[i];
-          if (((i & 255) >> 3) >= rows_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 h, l;
-          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-          bh[i] = h;
-          bl[i] = l;
-        }
         tmem_st_wait();
         tc_fence_before();
       } else {
@@ -1065,14 +1072,19 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
     // ===================== promoter / epilogue warps (6..13) =====================
     // Two warps per TMEM lane quarter; the pair alternates the tile's 16-column units.  Running sums of up to 4 units
     // (64 columns) per thread in registers; every finished chain is added in with round-to-nearest.
+    // TS: these 256 threads also split the X tile (B operand) of EVERY K-block in place — the four converter warps alone,
+    // doing dY^T and X one after the other, ran at 2,170 cycles per K-block against 1,125 of shared-memory-port time and
+    // 672 of tensor time.  A chunk is promoted 4 K-blocks after its last one was converted: the MMAs trail the converters
+    // by at most the ring depth, so that wait never stalls the conversion.
     const int q = warp & 3;
     const int half = (warp - 6) >> 2;
+    const int pt = threadIdx.x - 192;                // 0..255
     float sum[4][16];
 #pragma unroll
     for (int uu = 0; uu < 4; ++uu)
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) sum[uu][jj] = 0.f;
-    for (int32_t c = 0; c < n_chunks; ++c) {
+    auto promote = [&](int32_t c) {
       const uint32_t ab = (uint32_t)c & 1u;
       mbar_wait(&acc_full[ab], ((uint32_t)c >> 1) & 1u);
       tc_fence_after();
@@ -1089,7 +1101,33 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
+    };
+    int32_t next_chunk = 0;
+    if (TS) {
+      StageIter si{0, 0u, p.stages};
+      const int b4 = (int)(b_bytes / 16);
+      for (int32_t it = 0; it < KB; ++it, si.next()) {
+        const int s = si.s;
+        mbar_wait(&full_raw[s], si.ph);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const int32_t rows_ok = n - (kb_beg + it) * TW_KB;
+        // split in place (hi) + lo plane; float4 i of a box belongs to reduction row (i % 256) / 8; rows >= n are zeroed
+        float4* bh = reinterpret_cast<float4*>(st + a_span);
+        float4* bl = reinterpret_cast<float4*>(st + a_span + b_bytes);
+        for (int i = pt; i < b4; i += 32 * TW_EPI_WARPS) {
+          float4 x = bh[i];
+          if (((i & 255) >> 3) >= rows_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 h, l;
+          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+          bh[i] = h;
+          bl[i] = l;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full_conv[s]);
+        if (it >= TW_CHUNK + 4 && ((it - 4) % TW_CHUNK) == 0) promote(next_chunk++);
+      }
     }
+    while (next_chunk < n_chunks) promote(next_chunk++);
     // partial tile -> global, coalesced through a shared-memory staging patch (the ring is idle by now: every K-block of
     // this CTA has been consumed by MMAs that completed before the last acc_full)
     const int64_t row0 = (int64_t)o0 + q * 32;

@@ -27,7 +27,11 @@ namespace ngnn {
 
 constexpr int kMaxFanout = 64;   // Floyd's set lives in per-thread local storage
 constexpr int kMaxTranspose = 4; // hop prefixes whose CSC a block can carry
-constexpr int kDrawTile = 256;   // frontier nodes per CTA of k_hop_draw
+constexpr int kDrawTile = 64;    // frontier nodes per CTA of k_hop_draw: 8 warps x 8 nodes.  The draw is a chain of dependent
+                                 // global loads per node (neighbour id -> relabel slot), so what matters is how many nodes are
+                                 // in flight: 256 nodes per CTA (32 per warp, one after the other) took 79 us on the 76.8 k
+                                 // frontier of a products block, one node per warp (round 1) 14 us.
+constexpr int kDrawThreads = 256;
 constexpr int kScanTile = 1024;  // positions per CTA of k_hop_assign / k_tscan (256 threads x 4)
 constexpr int kSortSmem = 4096;  // longest transposed row sorted in shared memory by a CTA
 
@@ -198,7 +202,7 @@ struct DrawArgs {
 // every lane reads ITS neighbour id and relabel slot at once — one round of dependent DRAM latencies per node instead of
 // one per draw.  !WARP: one thread per node, any fan-out.  Same positions, emission order and Philox stream as the C oracle.
 template <bool WARP>
-__global__ void __launch_bounds__(kDrawTile) k_hop_draw(const DrawArgs a) {
+__global__ void __launch_bounds__(kDrawThreads) k_hop_draw(const DrawArgs a) {
   __shared__ int s_v[kDrawTile], s_beg[kDrawTile], s_d[kDrawTile], s_off[kDrawTile];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int32_t h = a.h, H = a.H, fanout = a.fanout, replace = a.replace;
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(kDrawTile) k_hop_draw(const DrawArgs a) {
   const int tile = take_ticket(a.ticket);
   const int64_t i = (int64_t)tile * kDrawTile + tid;
   int32_t v = -1, beg = 0, d = 0, k = 0;
-  if (i < fr) {
+  if (tid < kDrawTile && i < fr) {
     v = a.n_id[lo + i];
     beg = __ldg(a.colptr + v);
     d = __ldg(a.colptr + v + 1) - beg;
@@ -219,8 +223,8 @@ __global__ void __launch_bounds__(kDrawTile) k_hop_draw(const DrawArgs a) {
   }
   const TileScan sc = tile_scan_256(k, tile, a.state);
   const int32_t off = sc.excl;
-  if (tile == (int)gridDim.x - 1 && tid == kDrawTile - 1) a.counts[H + 2 + h] = e_base + sc.total;   // edges after this hop
-  if (i < fr) a.rowptr[lo + i + 1] = e_base + off + k;
+  if (tile == (int)gridDim.x - 1 && tid == kDrawThreads - 1) a.counts[H + 2 + h] = e_base + sc.total;   // edges after this hop
+  if (tid < kDrawTile && i < fr) a.rowptr[lo + i + 1] = e_base + off + k;
 
   if (!WARP) {
     // one thread per node
@@ -260,11 +264,12 @@ __global__ void __launch_bounds__(kDrawTile) k_hop_draw(const DrawArgs a) {
     return;
   }
 
-  // one warp per node of the tile
-  s_v[tid] = v; s_beg[tid] = beg; s_d[tid] = d; s_off[tid] = off;
+  // one warp per node of the tile, 8 nodes per warp
+  if (tid < kDrawTile) { s_v[tid] = v; s_beg[tid] = beg; s_d[tid] = d; s_off[tid] = off; }
   __syncthreads();
   const unsigned full = 0xffffffffu;
-  for (int jn = warp; jn < kDrawTile; jn += kDrawTile / 32) {
+#pragma unroll 2
+  for (int jn = warp; jn < kDrawTile; jn += kDrawThreads / 32) {
     const int32_t nv = s_v[jn];
     if (nv < 0) continue;                                      // warp-uniform
     const int32_t nbeg = s_beg[jn], nd = s_d[jn], noff = s_off[jn];
@@ -594,8 +599,8 @@ int32_t ngnn_sample_block_ex(const int32_t* colptr, const int32_t* row, int64_t 
     a.rowptr = rowptr; a.col_global = col_global; a.e_pos = e_pos; a.edge_dst = edge_dst;
     a.local_of = w.local_of; a.first_pos = w.first_pos; a.state = w.st_draw[h]; a.ticket = w.tickets + 2 * h;
     const unsigned gd = (unsigned)draw_tiles(c.fr_max[h]);
-    if (fanouts[h] <= 32) k_hop_draw<true><<<gd, kDrawTile, 0, st>>>(a);
-    else k_hop_draw<false><<<gd, kDrawTile, 0, st>>>(a);
+    if (fanouts[h] <= 32) k_hop_draw<true><<<gd, kDrawThreads, 0, st>>>(a);
+    else k_hop_draw<false><<<gd, kDrawThreads, 0, st>>>(a);
     NGNN_LAUNCH_CHECK();
     k_hop_assign<<<(unsigned)scan_tiles(c.e_max[h]), 256, 0, st>>>(col_global, counts, h, H, w.local_of, w.first_pos, n_id,
                                                                  w.st_assign[h], w.tickets + 2 * h + 1);

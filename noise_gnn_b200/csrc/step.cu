@@ -19,6 +19,7 @@ struct LayerPlan {
   int64_t F, O;                 // in / out channels
   int64_t ldo;                  // leading dimension of this layer's out / dy buffers (O rounded up to 4: TMA-addressable)
   int64_t ldf;                  // leading dimension of this layer's mean / root / dmean buffers (F rounded up to 4)
+  bool concat;                  // layer 1: mean and root rows side by side in ONE [n_dst, 2F] buffer (one K = 2F contraction)
   int a, b;                     // hop indices of this layer's extents: n_dst = nodes[a], e_lim = edges[b], n_src = nodes[b]
   int64_t n_dst, e_lim, n_src;  // trimmed extents of this step (host mode; = the capacities in device mode)
   int64_t n_dst_max, e_max, n_src_max;
@@ -51,6 +52,8 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     lp.O = i == L - 1 ? m->out_dim : m->hidden_dim;
     lp.ldo = (lp.O + 3) / 4 * 4;
     lp.ldf = (lp.F + 3) / 4 * 4;
+    lp.concat = i == 0 && lp.F % 4 == 0 && (2 * lp.F + 31) / 32 < 2 * ((lp.F + 31) / 32);   // only where it saves a K-block
+    if (lp.concat) lp.ldf = 2 * lp.F;
     const int d = L - 1 - i;   // hops between this layer's outputs and the seeds
     const int a = d < H ? d : H, b = d + 1 < H ? d + 1 : H;
     lp.a = a; lp.b = b;
@@ -62,7 +65,7 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     lp.off_b = poff; poff += (size_t)lp.O;
     lp.off_wr = poff; poff += (size_t)lp.O * lp.F;
     lp.mean = take((size_t)lp.n_dst_max * lp.ldf * 4);
-    lp.root = i == 0 ? take((size_t)lp.n_dst_max * lp.ldf * 4) : 0;
+    lp.root = i == 0 ? (lp.concat ? lp.mean + (size_t)lp.F * 4 : take((size_t)lp.n_dst_max * lp.ldf * 4)) : 0;
     lp.out = take((size_t)lp.n_dst_max * lp.ldo * 4);
     lp.dy = take((size_t)lp.n_dst_max * lp.ldo * 4);
     if (i > 0) {
@@ -197,7 +200,7 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
   prep_batch_begin();
   for (int i = 0; i < L; ++i) {
     const LayerPlan& lp = pl.layer[i];
-    rc = prep_batch_add(0, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_fwd, lp.prep_fwd_bytes);
+    rc = prep_batch_add(lp.concat ? 2 : 0, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_fwd, lp.prep_fwd_bytes);
     if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
     prep_fwd_ok[i] = rc == NGNN_OK;
     prep_dg_ok[i] = false;
@@ -239,7 +242,7 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
     rc = gemm_fwd_impl(F32(lp.mean), lp.ldf, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
                        n_dst.cap, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
                        drop_offset + (uint64_t)i, F32(lp.out), lp.ldo, nullptr, base + lp.prep_fwd, lp.prep_fwd_bytes,
-                       st, prep_fwd_ok[i], n_dst.dev, ctl, (uint32_t)i);
+                       st, prep_fwd_ok[i], n_dst.dev, ctl, (uint32_t)i, lp.concat && prep_fwd_ok[i]);
     if (rc != NGNN_OK) return rc;
   }
   const LayerPlan& top = pl.layer[L - 1];
