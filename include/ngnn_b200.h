@@ -292,6 +292,10 @@ typedef struct {
   const int32_t* counts;
   int32_t        batch_size;
   const ngnn_step_ctl_t* ctl;
+  /* 0: the step runs layer 1's aggregation itself; 1 / 2: the caller already ran ngnn_sage_agg1 for this block into copy
+   * 0 / 1 of the arena's layer-1 buffers (it depends on the block and the table only, so it can run for the NEXT block
+   * beside the current block's step: an HBM-bound gather under tensor-bound GEMMs).                              */
+  int32_t        agg1_buffer;
 } ngnn_block_t;
 
 int64_t ngnn_sage_num_params(const ngnn_sage_model_t* model);
@@ -314,6 +318,13 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
                        const int64_t* target_global, const int64_t* label_global,
                        uint64_t drop_seed, uint64_t drop_offset, float* stats /*[2]*/,
                        float* logits_out, int64_t ld_logits, void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* Layer 1's aggregation alone (mean of the sampled in-neighbours + root gather from the resident table) into copy `buffer`
+ * (0 / 1) of the arena's layer-1 buffers; consumed by a later ngnn_sage_step / _forward / _backward on the same arena whose
+ * block carries agg1_buffer = buffer + 1.                                                                          */
+int32_t ngnn_sage_agg1(const ngnn_sage_model_t* model, const ngnn_block_t* block, const int64_t* max_hop_nodes,
+                       const int64_t* max_hop_edges, const float* table, int64_t ld_table, int32_t buffer,
+                       void* ws, size_t ws_bytes, ngnn_stream_t stream);
 
 /* The step in two calls, for losses that couple several networks (co-teaching, reference src/pipeline.py:95-142: two
  * forwards, one joint loss, two backwards).  ngnn_sage_forward = the training-mode forward of ngnn_sage_step (dropout

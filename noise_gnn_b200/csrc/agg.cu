@@ -113,16 +113,20 @@ __device__ __forceinline__ void seg_finish(const AggParams& p, int64_t row, int 
 // slices are combined through shared memory in warp order (still atomic-free and run-to-run deterministic).
 constexpr int kLongRow = 1024;
 constexpr int kLongWarps = 8;
+template <int G, int VPL>
+constexpr int seg_max_threads() { return (G == 16 && VPL == 4) ? 128 : 512; }   // the half-warp-per-row variant runs small CTAs
 template <int G, int VPL, int U>
-__global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
+__global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(AggParams p) {
   constexpr int GROUPS_PER_WARP = 32 / G;
-  constexpr bool COOP = (G == 32);
+  // hub rows are handed to the whole CTA, a full warp per slice: CV vectors per lane cover the same G*VPL columns of a pass
+  constexpr bool COOP = (G >= 16) && (G * VPL >= 32);
+  constexpr int CV = COOP ? G * VPL / 32 : 1;
   // VPL == 4 (F 260..512): the 2 x VPL float4 of prefetch registers drop the kernel from 3 to 2 CTAs per SM (measured
   // 2.5x slower on the C5 sweep); VPL == 8 is at 2 CTAs per SM either way and measured faster with the prefetch.
   constexpr bool PRE = (VPL != 4);
   constexpr int NPRE = PRE ? VPL : 1;
-  __shared__ float4 s_part[COOP ? kLongWarps : 1][COOP ? VPL * 32 : 1];
-  __shared__ int s_long[16];
+  __shared__ float4 s_part[COOP ? kLongWarps : 1][COOP ? CV * 32 : 1];
+  __shared__ int s_long[64];
   __shared__ int s_nlong;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);                 // lane within group
@@ -175,32 +179,32 @@ __global__ void __launch_bounds__(512) k_seg_reduce_v4(AggParams p) {
   }
   if (COOP) {
     const int wib = threadIdx.x >> 5, nw = min((int)(blockDim.x >> 5), kLongWarps);
-    if (is_long && lane == 0) s_long[atomicAdd(&s_nlong, 1)] = wib;       // list order is irrelevant to each row's result
+    if (is_long && gl == 0) s_long[atomicAdd(&s_nlong, 1)] = wib * GROUPS_PER_WARP + gw;   // list order is irrelevant to each row's result
     __syncthreads();
     const int nlong = s_nlong;                                            // CTA-uniform
     for (int k = 0; k < nlong; ++k) {
-      const int64_t lrow = (int64_t)blockIdx.x * (blockDim.x >> 5) + s_long[k];
+      const int64_t lrow = (int64_t)blockIdx.x * (blockDim.x >> 5) * GROUPS_PER_WARP + s_long[k];
       const int lbeg = __ldg(p.ptr + lrow), lend = __ldg(p.ptr + lrow + 1);
       const int slice = ((lend - lbeg + nw - 1) / nw + 31) & ~31;          // whole 32-index windows per warp
       const int sb = min(lend, lbeg + wib * slice), se = wib < nw ? min(lend, sb + slice) : sb;
       const float scale = p.mean ? 1.0f / (float)max(lend - lbeg, 1) : 1.0f;
       const bool has_add = p.add != nullptr && lrow < agg_n_add(p);
-      for (int c0 = 0; c0 < F4; c0 += 32 * VPL) {
-        float4 acc[VPL];
+      for (int c0 = 0; c0 < F4; c0 += 32 * CV) {
+        float4 acc[CV];
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) acc[v] = zero4;
-        seg_accumulate<G, VPL, U>(p, sb, se, c0, F4, lane, 0xffffffffu, acc);
+        for (int v = 0; v < CV; ++v) acc[v] = zero4;
+        seg_accumulate<32, CV, U>(p, sb, se, c0, F4, lane, 0xffffffffu, acc);
         if (wib < nw) {
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) s_part[wib][v * 32 + lane] = acc[v];
+          for (int v = 0; v < CV; ++v) s_part[wib][v * 32 + lane] = acc[v];
         }
         __syncthreads();
         if (wib == 0) {
           const float4 none[1] = {zero4};
 #pragma unroll
-          for (int v = 0; v < VPL; ++v)
+          for (int v = 0; v < CV; ++v)
             for (int w = 1; w < nw; ++w) f4_add(acc[v], s_part[w][v * 32 + lane]);     // fixed warp order
-          seg_finish<G, VPL, false>(p, lrow, c0, F4, lane, scale, has_add, acc, none, none);
+          seg_finish<32, CV, false>(p, lrow, c0, F4, lane, scale, has_add, acc, none, none);
         }
         __syncthreads();
       }
@@ -369,10 +373,13 @@ static int g_tune_threads = 256; // ngnn_set_tuning(1, t): CTA size 128 / 256 / 
 static int g_tune_pipe = 1;      // ngnn_set_tuning(3, 0/1): software-pipelined persistent forward kernel
 static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 < F <= 128 (32 / 16 / 8)
 static int g_tune_keep = 1;      // ngnn_set_tuning(7, 0|1): L2 evict_last priority on the layer-1 table gathers
+static int g_tune_wide = 0;      // ngnn_set_tuning(9, v): generic kernel for 128 < F <= 256: 0 = half-warp/row x4 vectors, 128-thread
+                                 //   CTAs (default); 1 = warp/row x2 vectors unroll 2; 2 = warp/row unroll 4
 
 template <int G, int VPL, int U>
-static void launch_v4(const AggParams& p, cudaStream_t st) {
-  const int T = g_tune_threads;
+static void launch_v4(const AggParams& p, cudaStream_t st, int threads = 0) {
+  int T = threads > 0 && g_tune_threads == 256 ? threads : g_tune_threads;
+  if (T > seg_max_threads<G, VPL>()) T = seg_max_threads<G, VPL>();
   const int64_t rows_per_block = (T / 32) * (32 / G);
   k_seg_reduce_v4<G, VPL, U><<<(unsigned)ceil_div(p.n_rows, rows_per_block), T, 0, st>>>(p);
 }
@@ -417,7 +424,13 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
       else if (g_tune_group == 8) { if (u == 2) launch_v4<8, 4, 2>(p, st); else if (u == 8) launch_v4<8, 4, 8>(p, st); else launch_v4<8, 4, 4>(p, st); }
       else { if (u == 2) launch_v4<32, 1, 2>(p, st); else if (u == 8) launch_v4<32, 1, 8>(p, st); else launch_v4<32, 1, 4>(p, st); }
     }
-    else if (F4 <= 64) launch_v4<32, 2, 2>(p, st);
+    else if (F4 <= 64) {
+      // measured on the layer-2 backward of a products block (77 k rows x 256, mostly one transposed neighbour per row;
+      // profiles/prof_aggT.py): warp per row 61 us, half-warp per row with 128-thread CTAs 47 us (twice the rows in flight)
+      if (g_tune_wide == 2) launch_v4<32, 2, 4>(p, st);
+      else if (g_tune_wide == 1) launch_v4<32, 2, 2>(p, st);
+      else launch_v4<16, 4, 2>(p, st, 128);
+    }
     else if (F4 <= 128) launch_v4<32, 4, 2>(p, st);
     else launch_v4<32, 8, 1>(p, st);
   } else {
@@ -490,6 +503,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 3 && (value == 0 || value == 1)) { g_tune_pipe = value; return NGNN_OK; }
   if (key == 4 && (value == 128 || value == 256)) return ngnn_set_gemm_tile(value);
   if (key == 8 && value >= 0 && value <= 4096) return ngnn_set_wgrad_splits(value);
+  if (key == 9 && value >= 0 && value <= 2) { g_tune_wide = value; return NGNN_OK; }
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);

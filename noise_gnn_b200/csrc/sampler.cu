@@ -264,23 +264,25 @@ __global__ void __launch_bounds__(kDrawThreads) k_hop_draw(const DrawArgs a) {
     return;
   }
 
-  // one warp per node of the tile, 8 nodes per warp
+  // one warp per node of the tile, 8 nodes per warp.  The positions of all 8 nodes are decided first (registers only), then
+  // the 8 neighbour-id loads go out together, then the 8 relabel-map loads: two rounds of DRAM latency per warp instead of
+  // two per node.
   if (tid < kDrawTile) { s_v[tid] = v; s_beg[tid] = beg; s_d[tid] = d; s_off[tid] = off; }
   __syncthreads();
   const unsigned full = 0xffffffffu;
-#pragma unroll 2
-  for (int jn = warp; jn < kDrawTile; jn += kDrawThreads / 32) {
-    const int32_t nv = s_v[jn];
-    if (nv < 0) continue;                                      // warp-uniform
-    const int32_t nbeg = s_beg[jn], nd = s_d[jn], noff = s_off[jn];
-    const int32_t nk = replace ? (nd > 0 ? fanout : 0) : min(nd, fanout);
-    if (nk == 0) continue;
-    int32_t pos = lane;                                        // take all, stored order
-    if (replace || nd > fanout) {
+  constexpr int NPW = kDrawTile / (kDrawThreads / 32);       // nodes per warp
+  int32_t pos[NPW], g[NPW];
+#pragma unroll
+  for (int u = 0; u < NPW; ++u) {
+    const int jn = warp + u * (kDrawThreads / 32);
+    const int32_t nv = s_v[jn], nd = s_d[jn];
+    const int32_t nk = nv < 0 ? 0 : (replace ? (nd > 0 ? fanout : 0) : min(nd, fanout));
+    int32_t p = lane;                                          // take all, stored order
+    if (nk > 0 && (replace || nd > fanout)) {                  // warp-uniform
       const Philox4 r = philox4x32_10((uint32_t)nv, ((uint32_t)h << 16) | (uint32_t)(lane >> 2), batch_idx, epoch, a.seed_lo, a.seed_hi);
       const uint32_t w = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
       if (replace) {
-        pos = (int32_t)mulhi32(w, (uint32_t)nd);
+        p = (int32_t)mulhi32(w, (uint32_t)nd);
       } else {
         // Robert Floyd: for jj = d-k .. d-1: t = U[0,jj]; take t unless already taken, else take jj
         int32_t mine = -1;
@@ -291,17 +293,33 @@ __global__ void __launch_bounds__(kDrawThreads) k_hop_draw(const DrawArgs a) {
           if (__any_sync(full, lane < j && mine == t)) t = jj;
           if (lane == j) mine = t;
         }
-        pos = mine;
+        p = mine;
       }
     }
-    if (lane < nk) {
-      const int32_t g = __ldg(a.row + nbeg + pos);
-      const int32_t p = e_base + noff + lane;
-      a.col_global[p] = g;
+    pos[u] = lane < nk ? p : -1;
+  }
+#pragma unroll
+  for (int u = 0; u < NPW; ++u) {
+    const int jn = warp + u * (kDrawThreads / 32);
+    g[u] = pos[u] >= 0 ? __ldg(a.row + s_beg[jn] + pos[u]) : -1;
+  }
+  int32_t lof[NPW];
+#pragma unroll
+  for (int u = 0; u < NPW; ++u) {
+    const int jn = warp + u * (kDrawThreads / 32);
+    lof[u] = 0;
+    if (g[u] >= 0) {
+      const int32_t p = e_base + s_off[jn] + lane;
+      a.col_global[p] = g[u];
       if (a.edge_dst) a.edge_dst[p] = lo + tile * kDrawTile + jn;
-      if (a.e_pos) a.e_pos[p] = nbeg + pos;
-      if (a.local_of[g] < 0) atomicMin(a.first_pos + g, noff + lane);
+      if (a.e_pos) a.e_pos[p] = s_beg[jn] + pos[u];
+      lof[u] = a.local_of[g[u]];
     }
+  }
+#pragma unroll
+  for (int u = 0; u < NPW; ++u) {
+    const int jn = warp + u * (kDrawThreads / 32);
+    if (g[u] >= 0 && lof[u] < 0) atomicMin(a.first_pos + g[u], s_off[jn] + lane);
   }
 }
 

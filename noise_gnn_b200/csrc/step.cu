@@ -34,6 +34,7 @@ struct StepPlan {
   int L;
   LayerPlan layer[16];
   size_t dmean, droot, gemm_ws, dgrad_ws, wgrad_ws, wgrad_ws_aux, sort_ws, ce_rows, total;
+  size_t agg1_alt;              // byte distance from layer 1's [mean | root] buffer 0 to buffer 1 (ngnn_sage_agg1)
   size_t gemm_ws_bytes, dgrad_ws_bytes, wgrad_ws_bytes, sort_ws_bytes;
   int64_t n_params;
 };
@@ -66,6 +67,12 @@ static bool make_plan(const ngnn_sage_model_t* m, int32_t H, const int64_t* max_
     lp.off_wr = poff; poff += (size_t)lp.O * lp.F;
     lp.mean = take((size_t)lp.n_dst_max * lp.ldf * 4);
     lp.root = i == 0 ? (lp.concat ? lp.mean + (size_t)lp.F * 4 : take((size_t)lp.n_dst_max * lp.ldf * 4)) : 0;
+    if (i == 0) {     // a second copy of layer 1's aggregation buffers: the NEXT block's aggregation runs beside this block's step
+      const size_t first = lp.mean;
+      const size_t alt = take((size_t)lp.n_dst_max * lp.ldf * 4);
+      if (!lp.concat) take((size_t)lp.n_dst_max * lp.ldf * 4);
+      pl.agg1_alt = alt - first;
+    }
     lp.out = take((size_t)lp.n_dst_max * lp.ldo * 4);
     lp.dy = take((size_t)lp.n_dst_max * lp.ldo * 4);
     if (i > 0) {
@@ -169,6 +176,29 @@ size_t ngnn_sage_step_workspace_bytes(const ngnn_sage_model_t* model, int32_t nu
   return pl.total;
 }
 
+// Layer 1's aggregation: mean of the sampled in-neighbours + root gather, straight from the resident feature table by global
+// id, into copy `buffer` (0 / 1) of the arena's [mean | root] region.  It depends on the block and the table only — not on the
+// parameters — so a caller may run it for the NEXT block beside the current block's step (ngnn_sage_agg1).
+static int32_t agg1_launch(const ngnn_block_t* block, const StepPlan& pl, const float* table, int64_t ld_table, char* base,
+                           int buffer, cudaStream_t st) {
+  const LayerPlan& lp = pl.layer[0];
+  const bool dev = block->counts != nullptr;
+  const Ext n_dst = dev ? ext_dev(block->counts + lp.a, lp.n_dst_max) : ext_host(lp.n_dst);
+  const size_t off = buffer == 1 ? pl.agg1_alt : 0;
+  float* mean = reinterpret_cast<float*>(base + lp.mean + off);
+  float* root = reinterpret_cast<float*>(base + lp.root + off);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  const bool probe = g_probe_n < g_probe_cap && cap == cudaStreamCaptureStatusNone;
+  if (probe) cudaEventRecord(g_probe_ev[2 * g_probe_n], st);
+  const bool remapped = block->col_table != nullptr && block->n_table != nullptr;      // table stored hot rows first
+  const int32_t rc = agg_fwd_table_impl(block->rowptr, remapped ? block->col_table : block->col_global, table, ld_table, n_dst, lp.F,
+                                        mean, lp.ldf, remapped ? block->n_table : block->n_id, root, lp.ldf,
+                                        remapped ? block->hot_rows : -1, st);
+  if (probe) { cudaEventRecord(g_probe_ev[2 * g_probe_n + 1], st); ++g_probe_n; }
+  return rc;
+}
+
 // phase 0: forward + loss + backward (ngnn_sage_step); phase 1: training-mode forward only, activations stay in ws
 // (ngnn_sage_forward); phase 2: backward only from a caller-supplied top-layer gradient (ngnn_sage_backward).
 //
@@ -193,6 +223,7 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
   cudaStream_t st = as_stream(stream);
   // extent of "nodes within hop a" / "edges within hop b" for a kernel: device word + capacity, or the host value
   auto nodes_ext = [&](int a, int64_t cap, int64_t host) { return dev ? ext_dev(block->counts + a, cap) : ext_host(host); };
+  const size_t a1off = block->agg1_buffer == 2 ? pl.agg1_alt : 0;     // which copy of layer 1's [mean | root] this step reads
   int32_t rc;
 
   // ---------------- split weight planes of every layer: ONE launch, before the step's first kernel ----------------
@@ -222,16 +253,9 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
     const float* root;
     int64_t ld_root;
     if (i == 0) {   // aggregate from the resident table by global ids; gather the root rows in the same launch
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cap);
-      const bool probe = g_probe_n < g_probe_cap && cap == cudaStreamCaptureStatusNone;
-      if (probe) cudaEventRecord(g_probe_ev[2 * g_probe_n], st);
-      const bool remapped = block->col_table != nullptr && block->n_table != nullptr;      // table stored hot rows first
-      rc = agg_fwd_table_impl(block->rowptr, remapped ? block->col_table : block->col_global, table, ld_table, n_dst, lp.F,
-                              F32(lp.mean), lp.ldf, remapped ? block->n_table : block->n_id, F32(lp.root), lp.ldf,
-                              remapped ? block->hot_rows : -1, st);
-      if (probe) { cudaEventRecord(g_probe_ev[2 * g_probe_n + 1], st); ++g_probe_n; }
-      root = F32(lp.root); ld_root = lp.ldf;
+      rc = NGNN_OK;
+      if (block->agg1_buffer == 0) rc = agg1_launch(block, pl, table, ld_table, base, 0, st);   // else: done by ngnn_sage_agg1
+      root = F32(lp.root + a1off); ld_root = lp.ldf;
     } else {
       const LayerPlan& prev = pl.layer[i - 1];
       rc = agg_fwd_impl(block->rowptr, block->col, F32(prev.out), prev.ldo, n_dst, lp.F, F32(lp.mean), lp.ldf, st);
@@ -239,7 +263,7 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
     }
     if (rc != NGNN_OK) return rc;
     const bool last = i == L - 1;
-    rc = gemm_fwd_impl(F32(lp.mean), lp.ldf, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
+    rc = gemm_fwd_impl(F32(lp.mean + (i == 0 ? a1off : 0)), lp.ldf, root, ld_root, params + lp.off_wl, params + lp.off_wr, params + lp.off_b,
                        n_dst.cap, lp.F, lp.O, last ? NGNN_ACT_NONE : NGNN_ACT_RELU, last ? 0.f : p_drop, drop_seed,
                        drop_offset + (uint64_t)i, F32(lp.out), lp.ldo, nullptr, base + lp.prep_fwd, lp.prep_fwd_bytes,
                        st, prep_fwd_ok[i], n_dst.dev, ctl, (uint32_t)i, lp.concat && prep_fwd_ok[i]);
@@ -269,7 +293,8 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
   const bool use_aux = aux != nullptr;
   for (int i = L - 1; i >= 0; --i) {
     const LayerPlan& lp = pl.layer[i];
-    const float* root = i == 0 ? F32(lp.root) : F32(pl.layer[i - 1].out);
+    const float* root = i == 0 ? F32(lp.root + a1off) : F32(pl.layer[i - 1].out);
+    const float* mean = F32(lp.mean + (i == 0 ? a1off : 0));
     const int64_t ld_root = i == 0 ? lp.ldf : pl.layer[i - 1].ldo;
     // only the first bs rows of the top layer carry a gradient
     const Ext n_rows = i == L - 1 ? ext_host(bs) : nodes_ext(lp.a, lp.n_dst_max, lp.n_dst);
@@ -277,11 +302,11 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
       NGNN_CUDA(cudaEventRecord(aux->fork, st));
       NGNN_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
       aux_used = true;
-      rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
+      rc = wgrad_impl(F32(lp.dy), lp.ldo, mean, lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
                       grads + lp.off_wl, grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws_aux, pl.wgrad_ws_bytes,
                       aux->stream);
     } else {
-      rc = wgrad_impl(F32(lp.dy), lp.ldo, F32(lp.mean), lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
+      rc = wgrad_impl(F32(lp.dy), lp.ldo, mean, lp.ldf, root, ld_root, n_rows.cap, n_rows.dev, lp.F, lp.O,
                       grads + lp.off_wl, grads + lp.off_wr, grads + lp.off_b, 0, base + pl.wgrad_ws, pl.wgrad_ws_bytes, st);
     }
     if (rc != NGNN_OK) return rc;
@@ -323,6 +348,7 @@ static int32_t sage_step_impl(const ngnn_sage_model_t* model, const float* param
   NGNN_REQUIRE(dev || (block->hop_nodes && block->hop_edges), NGNN_E_INVALID, "sage_step: the block carries no extents");
   NGNN_REQUIRE(!dev || block->batch_size > 0, NGNN_E_INVALID, "sage_step: device-side extents need block->batch_size");
   NGNN_REQUIRE(model->dropout >= 0.f && model->dropout < 1.f, NGNN_E_INVALID, "sage_step: dropout outside [0,1)");
+  NGNN_REQUIRE(block->agg1_buffer >= 0 && block->agg1_buffer <= 2, NGNN_E_INVALID, "sage_step: agg1_buffer must be 0, 1 or 2");
   StepPlan pl;
   NGNN_REQUIRE(make_plan(model, block->num_hops, max_hop_nodes, max_hop_edges, dev ? nullptr : block->hop_nodes,
                          dev ? nullptr : block->hop_edges, pl),
@@ -352,6 +378,24 @@ static int32_t sage_step_impl(const ngnn_sage_model_t* model, const float* param
       return set_error(NGNN_E_CUDA, "sage_step: joining the auxiliary stream failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
   return rc;
+}
+
+int32_t ngnn_sage_agg1(const ngnn_sage_model_t* model, const ngnn_block_t* block, const int64_t* max_hop_nodes,
+                       const int64_t* max_hop_edges, const float* table, int64_t ld_table, int32_t buffer, void* ws, size_t ws_bytes,
+                       ngnn_stream_t stream) {
+  NGNN_REQUIRE(model && block && table && ws && max_hop_nodes && max_hop_edges, NGNN_E_INVALID, "sage_agg1: null pointer");
+  NGNN_REQUIRE(block->rowptr && block->col_global && block->n_id, NGNN_E_INVALID, "sage_agg1: incomplete block");
+  NGNN_REQUIRE(buffer == 0 || buffer == 1, NGNN_E_INVALID, "sage_agg1: buffer must be 0 or 1");
+  const bool dev = block->counts != nullptr;
+  NGNN_REQUIRE(dev || (block->hop_nodes && block->hop_edges), NGNN_E_INVALID, "sage_agg1: the block carries no extents");
+  StepPlan pl;
+  NGNN_REQUIRE(make_plan(model, block->num_hops, max_hop_nodes, max_hop_edges, dev ? nullptr : block->hop_nodes,
+                         dev ? nullptr : block->hop_edges, pl),
+               NGNN_E_INVALID, "sage_agg1: bad model / block extents");
+  NGNN_REQUIRE(ws_bytes >= pl.total, NGNN_E_WORKSPACE, "sage_agg1: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+  NGNN_REQUIRE(ld_table >= model->in_dim, NGNN_E_INVALID, "sage_agg1: ld_table < in_dim");
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  return agg1_launch(block, pl, table, ld_table, base, buffer, as_stream(stream));
 }
 
 int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,

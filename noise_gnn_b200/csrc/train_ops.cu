@@ -206,11 +206,17 @@ __global__ void __launch_bounds__(1024) k_ct_reduce(const float* __restrict__ sc
 __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                        float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
                        float weight_decay, float grad_scale, const int64_t* __restrict__ step_dev) {
+  // the two bias corrections (double-precision pow) once per CTA, not once per parameter
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_dev + 1);
+    s_bc[0] = (float)(1.0 - pow((double)beta1, t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, t));
+  }
+  __syncthreads();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double t = (double)(*step_dev + 1);
-  const float bc1 = (float)(1.0 - pow((double)beta1, t));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
   float g = grad[i] * grad_scale;
   const float p = param[i];
   if (weight_decay != 0.f) g += weight_decay * p;

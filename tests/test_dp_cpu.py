@@ -89,3 +89,28 @@ def test_two_rank_gradient_allreduce_matches_single_rank(tmp_path):
     assert all(abs(r["scale"] - 0.5) < 1e-12 for r in res)
     assert torch.equal(res[0]["reduced"], res[1]["reduced"])                  # every rank holds the same averaged gradient
     assert torch.allclose(res[0]["reduced"], res[0]["want"], rtol=1e-12, atol=1e-14)
+
+
+def test_ragged_and_padded_rounds_average_over_the_real_seeds():
+    """The last round of an epoch can hold a short batch and, on some ranks, a wrap-around filler: with the sharder's
+    loss_scale as the weight of each rank's MEAN, the all-reduced average (sum / R) is the mean over the round's real seeds
+    (pad the last round, mask padded seeds out of the loss).  Pure host arithmetic, no process group needed."""
+    n, bs = 10 * 16 + 5, 16                       # 11 global batches, the last with 5 seeds
+    vals = torch.randn(n, dtype=torch.float64)    # a per-seed quantity (stands in for the per-seed loss gradient)
+    nodes = torch.arange(n)
+    for R in (1, 2, 3, 4, 8):
+        shards = [SeedSharder(nodes, bs, True, 1232, rank=r, world_size=R) for r in range(R)]
+        order = shards[0].epoch_permutation(0)
+        steps = len(shards[0])
+        for i in range(steps):
+            real = [r for r in range(R) if i * R + r < shards[0].num_batches_global]
+            assert [s.is_padded(i) for s in shards] == [r not in real for r in range(R)]
+            seeds = [s.batch_seeds(order, s.global_batch_index(i)) for s in shards]
+            means = [vals[sd].mean() for sd in seeds]
+            got = sum(s.loss_scale(i) * m for s, m in zip(shards, means)) / R
+            want = torch.cat([seeds[r] for r in real])
+            assert abs(float(got) - float(vals[want].mean())) < 1e-12, (R, i)
+            assert abs(sum(s.loss_scale(i) for s in shards) - R) < 1e-9
+        # every real batch is trained exactly once per epoch
+        trained = sorted(s.global_batch_index(i) for s in shards for i in range(steps) if not s.is_padded(i))
+        assert trained == list(range(shards[0].num_batches_global))

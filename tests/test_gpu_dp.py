@@ -1,0 +1,104 @@
+"""Multi-GPU gradient equivalence on hardware (run with -m gpu on a box with >= 2 GPUs, e.g. `gpurun --gpus 2`; skipped on
+one GPU): R data-parallel ranks over NCCL — each sampling its own shard of the rank-agnostic batch sequence, all-reducing
+the flat gradient bucket — against ONE rank that processes the same global batches itself and averages their gradients."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _problem(dev, rank, world):
+    from noise_gnn_b200 import NeighborLoader, SAGE
+    from noise_gnn_b200.synthetic import make_dataset
+    data, sh, train_idx = make_dataset("arxiv", scale=0.05, device="cpu", noise_type="sym", noise_rate=0.3)
+    n_seeds = 32 * 11 + 5                      # 12 global batches: the last one short; with R = 2 an even split, R = 8 would pad
+    loader = NeighborLoader(data, input_nodes=train_idx[:n_seeds], num_neighbors=[10, 5], batch_size=32, shuffle=True, seed=1232,
+                            rank=rank, world_size=world, device=dev)
+    torch.manual_seed(1232)
+    net = SAGE(sh.features, 64, sh.classes, 3, dropout=0.0).to(dev)
+    net.train()
+    return loader, net
+
+
+def _rank_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from noise_gnn_b200.train import Trainer
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    loader, net = _problem(dev, rank, world)
+    tr = Trainer(net, lr=1e-3, world_size=world, rank=rank)
+    # (1) one round, gradients only: this rank's batch -> all-reduce -> mean
+    from noise_gnn_b200 import dp
+    order = loader.epoch_permutation(0)
+    batch = loader.sample(loader.batch_seeds(order, rank), epoch=0, batch_idx=rank)
+    tr.forward_backward(batch)
+    scale = dp.allreduce_mean_(tr.buckets.grad, None, world)
+    g1 = (tr.buckets.grad * scale).cpu()
+    tr.steps = 0
+    # (2) a whole epoch on the captured step
+    loss_sum, correct, log = tr.run_steps(loader, len(loader), start_epoch=0)       # eager steps, graph replays, ragged tail
+    torch.cuda.synchronize()
+    torch.save({"param": tr.buckets.param.cpu(), "grad": tr.buckets.grad.cpu(), "log": log.clone(), "replays": tr.graph_replays, "g1": g1},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_data_parallel_ranks_match_one_rank_on_the_same_global_batches(cuda_device, tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    from noise_gnn_b200 import ops
+    from noise_gnn_b200.train import Trainer
+    mp.spawn(_rank_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    # every rank applied the same all-reduced gradients: identical parameters, bit for bit
+    for r in range(1, world):
+        assert torch.equal(res[0]["param"], res[r]["param"])
+        assert torch.equal(res[0]["grad"], res[r]["grad"])
+    assert res[0]["replays"] > 0                                   # NCCL's all-reduce was captured in the replayed step
+    # one rank, the same global batches: per round, the size-weighted mean of the R batch gradients, then Adam
+    dev = cuda_device
+    loader, net = _problem(dev, 0, 1)
+    tr = Trainer(net, lr=1e-3, use_graph=False)
+    sh = loader.sharder
+    order = loader.epoch_permutation(0)
+    nb = sh.num_batches_global
+    # (1) the all-reduced gradient of round 0 == the mean of the gradients of global batches 0..R-1 computed by one rank
+    acc = torch.zeros_like(tr.buckets.grad)
+    for g in range(world):
+        tr.forward_backward(loader.sample(loader.batch_seeds(order, g), epoch=0, batch_idx=g))
+        acc += tr.buckets.grad / world
+    tr.steps = 0
+    for r in range(world):
+        assert torch.equal(res[r]["g1"], res[0]["g1"])
+    err = float((res[0]["g1"].double() - acc.double().cpu()).abs().max() / acc.double().abs().max())
+    assert err < 1e-6, err
+    for i in range(-(-nb // world)):
+        acc = torch.zeros_like(tr.buckets.grad)
+        real = [g for g in range(i * world, (i + 1) * world) if g < nb]
+        total = sum(sh.batch_len(g) for g in real)
+        for g in real:
+            batch = loader.sample(loader.batch_seeds(order, g), epoch=0, batch_idx=g)
+            tr.forward_backward(batch)
+            acc += tr.buckets.grad * (sh.batch_len(g) / total)
+        tr.buckets.grad.copy_(acc)
+        ops.adam_step(tr.buckets.param, tr.buckets.grad, tr.exp_avg, tr.exp_avg_sq, tr.step_dev, lr=1e-3)
+    got, want = res[0]["param"].double(), tr.buckets.param.double().cpu()
+    # Adam turns rounding-level gradient differences into +-lr steps on parameters whose gradient is ~0: compare at a few lr
+    assert float((got - want).abs().max()) < 12 * 1e-3 * 0.2
+    assert float((got - want).abs().mean()) < 2e-4

@@ -109,6 +109,7 @@ def test_device_extent_step_equals_host_extent_step(dev, L, fan, dropout):
     assert torch.equal(slot.counts.cpu(), batch._slot.counts.cpu())
     tr.reset_stats()
     tr.buckets.grad.zero_()
+    tr._enqueue_agg1(gs, 0, len(seeds))                       # layer 1's aggregation is its own call on this path
     bd = tr._slot_desc(gs, 0, len(seeds))
     ms, arena, table = gs["ms"], gs["arena"], gs["table"]
     _lib.call("ngnn_sage_step", ctypes.byref(ms), ops._ptr(tr.buckets.param), ops._ptr(tr.buckets.grad), ctypes.byref(bd),
