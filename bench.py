@@ -341,6 +341,12 @@ def run_ours(args):
         }
         _emit(real_stdout, out)
     if world > 1:
+        # the captured steps hold NCCL work: drop them before the group goes; a watchdog makes sure the process ends either way
+        t = threading.Timer(60.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        trainer.release_graphs()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -156,6 +156,14 @@ class SAGE(torch.nn.Module):
         node and hop), so the loader is asked for hop 1 only and K-AGG gathers straight from the [N, F] activation table
         by global id (no x[n_id] copy).  Seed-row outputs are the same function of the same sampled edges."""
         dev = subgraph_loader.device
+        nodes = subgraph_loader.input_nodes
+        if nodes.numel() != subgraph_loader.num_nodes or not torch.equal(nodes, torch.arange(nodes.numel())):
+            # every layer's output table is indexed by GLOBAL node id by the next layer (x_all[batch.n_id], reference
+            # sage.py:50): that is only meaningful when the loader walks all nodes in id order, as the reference's
+            # subgraph loaders do (input_nodes=None).  The reference would raise an IndexError or silently misalign here.
+            raise ValueError("SAGE.inference needs a loader over all nodes in id order (input_nodes=None, shuffle=False)")
+        if subgraph_loader.shuffle:
+            raise ValueError("SAGE.inference needs an unshuffled loader (rows of the layer outputs are node ids)")
         x_all = x_all.to(dev, dtype=torch.float32)
         last = self.num_layers - 1
         hops = list(subgraph_loader.num_neighbors)

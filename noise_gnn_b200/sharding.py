@@ -66,6 +66,13 @@ class SeedSharder:
         mine = self.batch_len(step * self.world_size + self.rank)
         return float(mine) * self.world_size / float(total) if total > 0 else 0.0
 
+    def round_is_full(self, step: int) -> bool:
+        """True when EVERY rank holds a real, full-size batch at local step `step`.  The captured (replayed) step is only used
+        for such rounds, so that all ranks take the same decision: a collective captured in a CUDA graph on one rank must not
+        meet an eagerly issued one on another."""
+        last = step * self.world_size + self.world_size - 1
+        return last < self.num_batches_global and self.batch_len(last) == self.batch_size
+
     def batch_seeds(self, order: torch.Tensor, global_batch_idx: int) -> torch.Tensor:
         b = global_batch_idx % max(self.num_batches_global, 1)
         return order[b * self.batch_size:(b + 1) * self.batch_size]

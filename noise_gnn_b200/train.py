@@ -210,6 +210,15 @@ class Trainer:
             self._gs = gs
         return gs
 
+    def release_graphs(self):
+        """Drop the captured steps (they are re-captured on demand).  Call before ``dist.destroy_process_group()``: a CUDA graph
+        that holds a captured NCCL all-reduce keeps the communicator busy, and tearing the group down under it hangs."""
+        if self._gs is not None:
+            self._gs["graphs"] = [None, None]
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     def _slot_desc(self, gs, k: int, bs: int):
         """ngnn_block_t over slot k with DEVICE-side extents (counts), the sampler-built transposes and the control words."""
         slot, loader = gs["slots"][k], gs["loader"]
@@ -309,7 +318,9 @@ class Trainer:
                 k = j & 1
                 bs_next = stage_block(j + 1, 1 - k) if j + 1 < n_steps else 0
                 self.steps += 1
-                full = bs_cur == bs_full and bs_next == bs_full
+                # replay only when this round and the next are full on EVERY rank (all ranks then agree on graph vs eager)
+                i_cur, i_next = (start_step + j) % spe, (start_step + j + 1) % spe
+                full = bs_next > 0 and sh.round_is_full(i_cur) and sh.round_is_full(i_next)
                 if self.use_graph and full and j >= 2:
                     if gs["graphs"][k] is None:
                         c0 = lib.ngnn_launch_count()

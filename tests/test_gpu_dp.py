@@ -40,6 +40,8 @@ def _rank_main(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     loader, net = _problem(dev, rank, world)
     tr = Trainer(net, lr=1e-3, world_size=world, rank=rank)
+    say = lambda *a: print(f"[rank {rank}]", *a, file=__import__("sys").stderr, flush=True)
+    say("setup done")
     # (1) one round, gradients only: this rank's batch -> all-reduce -> mean
     from noise_gnn_b200 import dp
     order = loader.epoch_permutation(0)
@@ -47,16 +49,22 @@ def _rank_main(rank, world, port, out_dir):
     tr.forward_backward(batch)
     scale = dp.allreduce_mean_(tr.buckets.grad, None, world)
     g1 = (tr.buckets.grad * scale).cpu()
+    say("first round all-reduced")
     tr.steps = 0
     # (2) a whole epoch on the captured step
     loss_sum, correct, log = tr.run_steps(loader, len(loader), start_epoch=0)       # eager steps, graph replays, ragged tail
     torch.cuda.synchronize()
+    say("epoch done, replays", tr.graph_replays)
     torch.save({"param": tr.buckets.param.cpu(), "grad": tr.buckets.grad.cpu(), "log": log.clone(), "replays": tr.graph_replays, "g1": g1},
                os.path.join(out_dir, f"r{rank}.pt"))
+    say("saved")
+    tr.release_graphs()                      # captured NCCL work must be gone before the group is torn down
     dist.barrier()
     dist.destroy_process_group()
+    say("group destroyed")
 
 
+@pytest.mark.timeout(420)
 @pytest.mark.parametrize("world", [2])
 def test_data_parallel_ranks_match_one_rank_on_the_same_global_batches(cuda_device, tmp_path, world):
     if torch.cuda.device_count() < world:
@@ -64,7 +72,14 @@ def test_data_parallel_ranks_match_one_rank_on_the_same_global_batches(cuda_devi
     import torch.multiprocessing as mp
     from noise_gnn_b200 import ops
     from noise_gnn_b200.train import Trainer
-    mp.spawn(_rank_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ctx = mp.spawn(_rank_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=False)
+    import time
+    t0 = time.time()
+    while not ctx.join(timeout=5):                   # a hung collective must not take the GPU box with it
+        if time.time() - t0 > 300:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("data-parallel ranks did not finish within 300 s")
     res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
     # every rank applied the same all-reduced gradients: identical parameters, bit for bit
     for r in range(1, world):

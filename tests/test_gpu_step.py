@@ -291,3 +291,15 @@ def test_ctloss_two_backwards_two_optimizers_like_the_reference(dev):
     opt2.zero_grad(); got[1].backward(); opt2.step()              # second backward through the same CTLoss call
     assert rel_err(g1, w1.grad) < 1e-5 and rel_err(a2.grad, w2.grad) < 1e-5
     assert rel_err(got[0].detach(), want[0].detach()) < 1e-5 and rel_err(got[1].detach(), want[1].detach()) < 1e-5
+
+
+def test_inference_rejects_loaders_that_do_not_walk_all_nodes_in_order(dev):
+    """Layer outputs are indexed by global node id by the next layer (reference sage.py:50): a subset or shuffled loader
+    would silently misalign rows, so it is refused."""
+    from noise_gnn_b200 import NeighborLoader
+    data, sh, loader, ref, net = _setup(dev, 3, [10, 5], dropout=0.0, scale=0.01)
+    net.eval()
+    with pytest.raises(ValueError, match="all nodes"):
+        net.inference(data.x, NeighborLoader(data, input_nodes=torch.arange(100), num_neighbors=[10, 5], batch_size=64), dev)
+    with pytest.raises(ValueError, match="unshuffled"):
+        net.inference(data.x, NeighborLoader(data, input_nodes=None, num_neighbors=[10, 5], batch_size=64, shuffle=True), dev)
