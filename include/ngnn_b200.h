@@ -60,7 +60,8 @@ typedef struct {
   uint32_t drop_offset_lo, drop_offset_hi;
   float    loss_scale;    /* weight of this batch's loss gradient: 1 on one GPU; data parallel: bs_r * R / sum_r bs_r, so that the
                              all-reduced mean is the GLOBAL-batch mean; 0 masks a padded (wrapped-around) batch out entirely */
-  uint32_t reserved[3];
+  uint32_t ticket;        /* library-internal arrival counter (zeroed by ngnn_step_ctl_set) */
+  uint32_t reserved[2];
 } ngnn_step_ctl_t;
 int32_t ngnn_step_ctl_set(ngnn_step_ctl_t* ctl /*device*/, uint32_t epoch, uint32_t batch_idx, uint64_t drop_offset,
                           float loss_scale, ngnn_stream_t stream);
@@ -191,7 +192,9 @@ int32_t ngnn_ce_fwd_bwd_gather(const float* logits, int64_t ld, const int64_t* t
 /* ---- optimizer (torch.optim.Adam(lr), reference src/models/model.py:67-69) ----
  * One fused pass over a flat parameter bucket; step_count is the 1-based step t held in a
  * device int64 (so a captured graph can be replayed): the kernel reads *step_dev, and the
- * thread (0,0) increments it when advance_step != 0.                                         */
+ * a follow-up one-thread launch increments it when advance_step == 1; advance_step == 2: step_dev
+ * points at TWO int64 words, the second a zero-initialised ticket, and the last CTA of the Adam
+ * kernel itself advances the counter (one launch).                                              */
 int32_t ngnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                        float lr, float beta1, float beta2, float eps, float weight_decay,
                        float grad_scale, int64_t* step_dev, int32_t advance_step, ngnn_stream_t stream);
@@ -296,6 +299,9 @@ typedef struct {
    * 0 / 1 of the arena's layer-1 buffers (it depends on the block and the table only, so it can run for the NEXT block
    * beside the current block's step: an HBM-bound gather under tensor-bound GEMMs).                              */
   int32_t        agg1_buffer;
+  /* != 0: ngnn_sage_prep_weights already split this step's parameters into the arena (it only depends on the parameters, so
+   * a caller can run it on another stream beside ngnn_sage_agg1); the step then skips its own weight-pack launch.   */
+  int32_t        weights_prepared;
 } ngnn_block_t;
 
 int64_t ngnn_sage_num_params(const ngnn_sage_model_t* model);
@@ -325,6 +331,12 @@ int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, floa
 int32_t ngnn_sage_agg1(const ngnn_sage_model_t* model, const ngnn_block_t* block, const int64_t* max_hop_nodes,
                        const int64_t* max_hop_edges, const float* table, int64_t ld_table, int32_t buffer,
                        void* ws, size_t ws_bytes, ngnn_stream_t stream);
+
+/* The step's weight pack alone: hi / lo (3xTF32) K-major planes of every layer's [W_l | W_r] and, for the data gradients,
+ * [W_l^T ; W_r^T], written into the arena.  One launch; depends on the parameters only.                              */
+int32_t ngnn_sage_prep_weights(const ngnn_sage_model_t* model, const float* params, int32_t num_hops,
+                               const int64_t* max_hop_nodes, const int64_t* max_hop_edges, void* ws, size_t ws_bytes,
+                               ngnn_stream_t stream);
 
 /* The step in two calls, for losses that couple several networks (co-teaching, reference src/pipeline.py:95-142: two
  * forwards, one joint loss, two backwards).  ngnn_sage_forward = the training-mode forward of ngnn_sage_step (dropout

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ngnn_sample_block_ex": (c_int32, [_P, _P, c_int64, _P, c_int32, _P, c_int32, c_int32, c_uint64, c_uint32, c_uint32, _P,
                                        _P, _P, _P, _P, _P, _P, _P, c_int32, _P, _P, _P, c_size_t, _P]),
     "ngnn_step_ctl_set": (c_int32, [_P, c_uint32, c_uint32, c_uint64, c_float, _P]),
+    "ngnn_sage_prep_weights": (c_int32, [_P, _P, c_int32, _P, _P, _P, c_size_t, _P]),
     "ngnn_sage_agg1": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32, _P, c_size_t, _P]),
     "ngnn_block_table_index": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, _P, _P, _P]),
     "ngnn_sage_forward": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_uint64, c_uint64, _P, c_int64, _P, c_size_t, _P]),
@@ -83,7 +84,8 @@ class BlockDesc(ctypes.Structure):      # ngnn_block_t
                 ("num_hops", c_int32), ("hop_nodes", ctypes.POINTER(c_int32)), ("hop_edges", ctypes.POINTER(c_int32)),
                 ("colptr_t", c_void_p * 8), ("row_t", c_void_p * 8),
                 ("col_table", c_void_p), ("n_table", c_void_p), ("hot_rows", c_int64),
-                ("counts", c_void_p), ("batch_size", c_int32), ("ctl", c_void_p), ("agg1_buffer", c_int32)]
+                ("counts", c_void_p), ("batch_size", c_int32), ("ctl", c_void_p), ("agg1_buffer", c_int32),
+                ("weights_prepared", c_int32)]
 
 
 _lib = None

@@ -68,7 +68,8 @@ struct StepCtl {
   uint32_t epoch, batch_idx;
   uint32_t drop_off_lo, drop_off_hi;
   uint32_t loss_scale_bits;      // float: weight of this batch's loss gradient (data parallel: bs_r * R / sum bs; 0 = padded batch)
-  uint32_t reserved[3];
+  uint32_t ticket;               // arrival counter of the loss kernel's CTAs (the last one reduces); zeroed by ngnn_step_ctl_set
+  uint32_t reserved[2];
 };
 
 // Library-internal entry points of the dense kernels (gemm.cu) for the fused step (step.cu): the split weight planes

@@ -518,6 +518,7 @@ __global__ void k_table_index(const int32_t* __restrict__ remap, const int32_t* 
 __global__ void k_step_ctl_set(StepCtl* ctl, uint32_t epoch, uint32_t batch_idx, uint32_t off_lo, uint32_t off_hi, float loss_scale) {
   ctl->epoch = epoch; ctl->batch_idx = batch_idx; ctl->drop_off_lo = off_lo; ctl->drop_off_hi = off_hi;
   ctl->loss_scale_bits = __float_as_uint(loss_scale);
+  ctl->ticket = 0u;
 }
 
 }  // namespace ngnn

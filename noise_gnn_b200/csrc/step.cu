@@ -176,6 +176,26 @@ size_t ngnn_sage_step_workspace_bytes(const ngnn_sage_model_t* model, int32_t nu
   return pl.total;
 }
 
+// Collects the weight-pack jobs of every layer (forward packs; data-gradient packs of layers >= 2 when training) into the
+// thread's batch; which layers take the tensor-core path comes back in the two flag arrays.  prep_batch_launch runs them.
+static int32_t prep_weights_collect(const StepPlan& pl, const float* params, bool train, char* base, bool* prep_fwd_ok,
+                                    bool* prep_dg_ok) {
+  prep_batch_begin();
+  for (int i = 0; i < pl.L; ++i) {
+    const LayerPlan& lp = pl.layer[i];
+    int32_t rc = prep_batch_add(lp.concat ? 2 : 0, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_fwd, lp.prep_fwd_bytes);
+    if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
+    prep_fwd_ok[i] = rc == NGNN_OK;
+    prep_dg_ok[i] = false;
+    if (train && i > 0) {
+      rc = prep_batch_add(1, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_dg, lp.prep_dg_bytes);
+      if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
+      prep_dg_ok[i] = rc == NGNN_OK;
+    }
+  }
+  return NGNN_OK;
+}
+
 // Layer 1's aggregation: mean of the sampled in-neighbours + root gather, straight from the resident feature table by global
 // id, into copy `buffer` (0 / 1) of the arena's [mean | root] region.  It depends on the block and the table only — not on the
 // parameters — so a caller may run it for the NEXT block beside the current block's step (ngnn_sage_agg1).
@@ -228,21 +248,10 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
 
   // ---------------- split weight planes of every layer: ONE launch, before the step's first kernel ----------------
   bool prep_fwd_ok[16], prep_dg_ok[16];
-  prep_batch_begin();
-  for (int i = 0; i < L; ++i) {
-    const LayerPlan& lp = pl.layer[i];
-    rc = prep_batch_add(lp.concat ? 2 : 0, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_fwd, lp.prep_fwd_bytes);
-    if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
-    prep_fwd_ok[i] = rc == NGNN_OK;
-    prep_dg_ok[i] = false;
-    if (train && i > 0) {
-      rc = prep_batch_add(1, params + lp.off_wl, params + lp.off_wr, lp.F, lp.O, base + lp.prep_dg, lp.prep_dg_bytes);
-      if (rc != NGNN_OK && rc != NGNN_E_UNSUPPORTED) return rc;
-      prep_dg_ok[i] = rc == NGNN_OK;
-    }
-  }
-  if (phase != 2) {          // phase 2: the planes of the matching forward call are still valid (weights unchanged)
-    rc = prep_batch_launch(st);
+  rc = prep_weights_collect(pl, params, train, base, prep_fwd_ok, prep_dg_ok);
+  if (rc != NGNN_OK) return rc;
+  if (phase != 2 && !block->weights_prepared) {   // phase 2: the planes of the matching forward call are still valid;
+    rc = prep_batch_launch(st);                    // weights_prepared: ngnn_sage_prep_weights already ran for these parameters
     if (rc != NGNN_OK) return rc;
   }
 
@@ -396,6 +405,20 @@ int32_t ngnn_sage_agg1(const ngnn_sage_model_t* model, const ngnn_block_t* block
   NGNN_REQUIRE(ld_table >= model->in_dim, NGNN_E_INVALID, "sage_agg1: ld_table < in_dim");
   char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(ws), 256));
   return agg1_launch(block, pl, table, ld_table, base, buffer, as_stream(stream));
+}
+
+int32_t ngnn_sage_prep_weights(const ngnn_sage_model_t* model, const float* params, int32_t num_hops, const int64_t* max_hop_nodes,
+                               const int64_t* max_hop_edges, void* ws, size_t ws_bytes, ngnn_stream_t stream) {
+  NGNN_REQUIRE(model && params && ws && max_hop_nodes && max_hop_edges, NGNN_E_INVALID, "sage_prep_weights: null pointer");
+  StepPlan pl;
+  NGNN_REQUIRE(make_plan(model, num_hops, max_hop_nodes, max_hop_edges, nullptr, nullptr, pl), NGNN_E_INVALID,
+               "sage_prep_weights: bad model / capacities");
+  NGNN_REQUIRE(ws_bytes >= pl.total, NGNN_E_WORKSPACE, "sage_prep_weights: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(ws), 256));
+  bool f_ok[16], d_ok[16];
+  const int32_t rc = prep_weights_collect(pl, params, true, base, f_ok, d_ok);
+  if (rc != NGNN_OK) return rc;
+  return prep_batch_launch(as_stream(stream));
 }
 
 int32_t ngnn_sage_step(const ngnn_sage_model_t* model, const float* params, float* grads, const ngnn_block_t* block,

@@ -19,6 +19,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ void ct_row_stats(const float* row, int64_t C, int lane, int64_t tgt, float& loss, float& lse, int64_t& arg);
+
 // One warp per row: log-sum-exp, gradient row, per-row loss / correct flag into `rows` ([2*bs]).
 __global__ void __launch_bounds__(256) k_ce_rows(const float* __restrict__ logits, int64_t ld,
                                                  const int64_t* __restrict__ target, const int64_t* __restrict__ y_true,
@@ -60,6 +62,61 @@ __global__ void __launch_bounds__(256) k_ce_rows(const float* __restrict__ logit
     rows[i] = lse - row[tgt];
     rows[bs + i] = (y_true != nullptr && arg == y_true[li]) ? 1.f : 0.f;
   }
+}
+
+// fixed-order tree sum of the per-row values by one CTA (any block size that is a power of two <= 1024)
+__device__ __forceinline__ void ce_reduce_cta(const float* rows, int64_t bs, float* stats, float* s_l, float* s_c) {
+  const int T = blockDim.x;
+  float l = 0.f, c = 0.f;
+  for (int64_t i = threadIdx.x; i < bs; i += T) { l += rows[i]; c += rows[bs + i]; }
+  s_l[threadIdx.x] = l; s_c[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = T >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { s_l[threadIdx.x] += s_l[threadIdx.x + o]; s_c[threadIdx.x] += s_c[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { stats[0] += s_l[0] / (float)bs; stats[1] += s_c[0]; }
+}
+
+// k_ce_rows + the reduction in ONE launch (replayed step): the CTA that finishes last (a ticket in the step's control words,
+// reset by ngnn_step_ctl_set before every step) sums the rows in the same fixed order as k_ce_reduce with 256 threads.
+__global__ void __launch_bounds__(256) k_ce_rows_reduce(const float* __restrict__ logits, int64_t ld,
+                                                        const int64_t* __restrict__ target, const int64_t* __restrict__ y_true,
+                                                        const int32_t* __restrict__ row_ids, int64_t bs, int64_t C,
+                                                        float grad_scale, float* rows, float* __restrict__ dlogits,
+                                                        int64_t ld_d, StepCtl* ctl, float* stats) {
+  __shared__ float s_l[256], s_c[256];
+  __shared__ int s_last;
+  const float w = __uint_as_float(ctl->loss_scale_bits);
+  grad_scale *= w;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (i < bs) {
+    const float* row = logits + i * ld;
+    const int64_t li = row_ids != nullptr ? (int64_t)row_ids[i] : i;
+    const int64_t tgt = target[li];
+    float loss, lse;
+    int64_t arg;
+    ct_row_stats(row, C, lane, tgt, loss, lse, arg);
+    if (dlogits != nullptr) {
+      const float g = grad_scale / (float)bs;
+      for (int64_t c = lane; c < C; c += 32) {
+        const float pr = expf(row[c] - lse);
+        dlogits[i * ld_d + c] = (pr - (c == tgt ? 1.f : 0.f)) * g;
+      }
+    }
+    if (lane == 0) {
+      rows[i] = loss;
+      rows[bs + i] = (y_true != nullptr && arg == y_true[li]) ? 1.f : 0.f;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (w != 0.f) ce_reduce_cta(rows, bs, stats, s_l, s_c);        // a padded (masked-out) batch is not logged
 }
 
 // Single CTA: fixed-order tree sum of the per-row values => bitwise reproducible loss.
@@ -203,9 +260,11 @@ __global__ void __launch_bounds__(1024) k_ct_reduce(const float* __restrict__ sc
   }
 }
 
+// ticket != nullptr: the CTA that finishes last advances *step_dev (every CTA has read it by then) and clears the ticket —
+// the counter moves without a second launch.
 __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                        float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, float grad_scale, const int64_t* __restrict__ step_dev) {
+                       float weight_decay, float grad_scale, int64_t* step_dev, unsigned int* ticket) {
   // the two bias corrections (double-precision pow) once per CTA, not once per parameter
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {
@@ -215,17 +274,22 @@ __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad
   }
   __syncthreads();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
-  float g = grad[i] * grad_scale;
-  const float p = param[i];
-  if (weight_decay != 0.f) g += weight_decay * p;
-  const float mi = m[i] + (g - m[i]) * (1.0f - beta1);
-  const float vi = beta2 * v[i] + (1.0f - beta2) * g * g;
-  m[i] = mi;
-  v[i] = vi;
-  const float denom = sqrtf(vi) / bc2_sqrt + eps;
-  param[i] = p - (lr / bc1) * (mi / denom);
+  if (i < n) {
+    const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+    float g = grad[i] * grad_scale;
+    const float p = param[i];
+    if (weight_decay != 0.f) g += weight_decay * p;
+    const float mi = m[i] + (g - m[i]) * (1.0f - beta1);
+    const float vi = beta2 * v[i] + (1.0f - beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    param[i] = p - (lr / bc1) * (mi / denom);
+  }
+  if (ticket != nullptr) {
+    __syncthreads();                               // thread 0's read of *step_dev above is behind this CTA
+    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) { *step_dev += 1; *ticket = 0u; }
+  }
 }
 
 __global__ void k_inc_step(int64_t* step_dev) { *step_dev += 1; }
@@ -246,6 +310,12 @@ int32_t ce_impl(const float* logits, int64_t ld, const int64_t* target, const in
   if (bs == 0 || C == 0) return NGNN_OK;
   NGNN_REQUIRE(logits && target && stats && row_scratch, NGNN_E_INVALID, "ce: null pointer");
   NGNN_REQUIRE(ld >= C && (dlogits == nullptr || ld_d >= C), NGNN_E_INVALID, "ce: leading dimension < C");
+  if (ctl != nullptr) {      // replayed step: one launch, the last CTA reduces (ticket in the control words)
+    k_ce_rows_reduce<<<(unsigned)ceil_div(bs * 32, 256), 256, 0, st>>>(logits, ld, target, y_true, row_ids, bs, C, grad_scale,
+                                                                         row_scratch, dlogits, ld_d, const_cast<StepCtl*>(ctl), stats);
+    NGNN_LAUNCH_CHECK();
+    return NGNN_OK;
+  }
   k_ce_rows<<<(unsigned)ceil_div(bs * 32, 256), 256, 0, st>>>(logits, ld, target, y_true, row_ids, bs, C, grad_scale, row_scratch,
                                                                 dlogits, ld_d, ctl);
   NGNN_LAUNCH_CHECK();
@@ -300,9 +370,12 @@ int32_t ngnn_adam_step(float* param, const float* grad, float* exp_avg, float* e
   cudaStream_t st = as_stream(stream);
   if (n > 0) {
     NGNN_REQUIRE(param && grad && exp_avg && exp_avg_sq, NGNN_E_INVALID, "adam: null pointer");
+    // advance_step == 2: step_dev[1] is a zero-initialised ticket word owned by this call sequence (no second launch)
+    unsigned int* ticket = advance_step == 2 ? reinterpret_cast<unsigned int*>(step_dev + 1) : nullptr;
     k_adam<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                       weight_decay, grad_scale, step_dev);
+                                                       weight_decay, grad_scale, step_dev, ticket);
     NGNN_LAUNCH_CHECK();
+    if (ticket != nullptr) return NGNN_OK;
   }
   if (advance_step) {
     k_inc_step<<<1, 1, 0, st>>>(step_dev);

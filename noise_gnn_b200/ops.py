@@ -354,7 +354,7 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr=1e-3, betas=(0.9, 0
     with _timed("adam"):
         _lib.call("ngnn_adam_step", _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
                   float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(grad_scale), _ptr(step_dev),
-                  int(advance_step), _stream())
+                  (2 if step_dev.numel() >= 2 else 1) if advance_step else 0, _stream())
 
 
 # ----------------------------------------------------------------------------- SAGEPL extras

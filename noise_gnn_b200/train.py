@@ -81,7 +81,7 @@ class Trainer:
         dev = self.buckets.param.device
         self.exp_avg = torch.zeros_like(self.buckets.param)
         self.exp_avg_sq = torch.zeros_like(self.buckets.param)
-        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_dev = torch.zeros(2, dtype=torch.int64, device=dev)    # [completed steps, ticket word of the Adam kernel]
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)     # [sum of step losses, #correct]
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.process_group, self.world_size = process_group, world_size
@@ -246,13 +246,20 @@ class Trainer:
         The same call sequence runs eagerly (first steps, ragged tail) and under graph capture."""
         loader, side = gs["loader"], gs["side"]
         cur = torch.cuda.current_stream()
+        ms, arena, table = gs["ms"], gs["arena"], gs["table"]
+        # the weight pack (depends on the parameters only) beside the aggregation (depends on the block only)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _lib.call("ngnn_sage_prep_weights", ctypes.byref(ms), ops._ptr(self.buckets.param), gs["H"], self._max_nodes,
+                      self._max_edges, ops._ptr(arena), arena.numel(), ops._stream())
         self._enqueue_agg1(gs, k, bs_cur)      # HBM-bound, alone on the GPU: the sampler is forked only behind it
+        cur.wait_stream(side)
         if bs_next > 0:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 loader.launch_sample(gs["slots"][1 - k], None, bs_next, 0, 0, use_ctl=True, transposes=gs["T"])
         bd = self._slot_desc(gs, k, bs_cur)
-        ms, arena, table = gs["ms"], gs["arena"], gs["table"]
+        bd.weights_prepared = 1
         _lib.call("ngnn_sage_step", ctypes.byref(ms), ops._ptr(self.buckets.param), ops._ptr(self.buckets.grad), ctypes.byref(bd),
                   self._max_nodes, self._max_edges, ops._ptr(table), table.stride(0), ops._ptr(gs["tgt"]), ops._ptr(gs["lab"]),
                   self._drop_seed(), 0, ops._ptr(self.stats), None, 0, ops._ptr(arena), arena.numel(), ops._stream())
