@@ -114,7 +114,9 @@ int32_t ngnn_gcn_agg_fwd(const int32_t* rowptr, const int32_t* col, const float*
  * aggregation kernel (128/256/512); 2: lanes per row for 64 < F <= 128 (32/16/8); 3: software-pipelined persistent K-AGG
  * (1 = default); 4: widest N tile of the tcgen05 GEMM (128 = default, 256); 6: A operand of the tcgen05 kernels in
  * tensor memory (1 = default) or shared memory (0); 7: L2 evict_last priority on the layer-1 table gathers (1 = default);
- * 8: number of reduction slices of the tcgen05 K-WGRAD (0 = automatic: one wave of CTAs). */
+ * 8: number of reduction slices of the tcgen05 K-WGRAD (0 = automatic: one wave of CTAs); 9: K-AGG-T variant for
+ * 128 < F <= 256 (0 = half-warp per row, default; 1 / 2 = warp per row, unroll 2 / 4); 10: programmatic dependent launch
+ * along the step's kernel chain (0 = off, default: measured slower). */
 int32_t ngnn_set_tuning(int32_t key, int32_t value);
 
 /* ---- K-AGG-T: transpose (CSC) segment sum, backward of K-AGG ----

@@ -15,6 +15,12 @@ int32_t set_error(int32_t code, const char* fmt, ...) {
   return code;
 }
 
+// ngnn_set_tuning(10, 0|1): programmatic dependent launch along the step's kernel chain.  OFF: measured on the products step
+// (profiles/r02_notes.md) it is SLOWER, 0.494 ms against 0.413 ms per step — the early-scheduled CTAs of the next kernel
+// (200 KB of shared memory, 57 k registers for a GEMM) sit on the SMs while they wait and keep the auxiliary stream's
+// weight-gradient kernels and the sampler's kernels from being scheduled beside the running kernel.
+int g_use_pdl = 0;
+
 static std::atomic<uint64_t> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

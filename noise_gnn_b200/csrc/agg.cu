@@ -117,6 +117,8 @@ template <int G, int VPL>
 constexpr int seg_max_threads() { return (G == 16 && VPL == 4) ? 128 : 512; }   // the half-warp-per-row variant runs small CTAs
 template <int G, int VPL, int U>
 __global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(AggParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int GROUPS_PER_WARP = 32 / G;
   // hub rows are handed to the whole CTA, a full warp per slice: CV vectors per lane cover the same G*VPL columns of a pass
   constexpr bool COOP = (G >= 16) && (G * VPL >= 32);
@@ -279,6 +281,8 @@ __global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
 // ---------------------------------------------------------------------------------------------------
 template <int VPL, int U, bool ROOT>
 __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = agg_rows(p);
@@ -365,7 +369,7 @@ static void launch_pipe(const AggParams& p, cudaStream_t st) {
   int64_t grid = (int64_t)kNumSMs * blocks_per_sm;                 // persistent: one resident wave
   const int64_t need = ceil_div(p.n_rows, 8);                        // 8 warps per CTA
   if (grid > need) grid = need;
-  k_agg_fwd_pipe<VPL, U, ROOT><<<(unsigned)grid, 256, 0, st>>>(p);
+  launch_chain(k_agg_fwd_pipe<VPL, U, ROOT>, dim3((unsigned)grid), dim3(256), 0, st, p);
 }
 
 static int g_tune_unroll = 0;    // ngnn_set_tuning(0, u): 0 = default, else force U in {2,4,8} for F <= 128
@@ -381,7 +385,7 @@ static void launch_v4(const AggParams& p, cudaStream_t st, int threads = 0) {
   int T = threads > 0 && g_tune_threads == 256 ? threads : g_tune_threads;
   if (T > seg_max_threads<G, VPL>()) T = seg_max_threads<G, VPL>();
   const int64_t rows_per_block = (T / 32) * (32 / G);
-  k_seg_reduce_v4<G, VPL, U><<<(unsigned)ceil_div(p.n_rows, rows_per_block), T, 0, st>>>(p);
+  launch_chain(k_seg_reduce_v4<G, VPL, U>, dim3((unsigned)ceil_div(p.n_rows, rows_per_block)), dim3(T), 0, st, p);
 }
 
 static int32_t run_agg(const AggParams& p, cudaStream_t st) {
@@ -504,6 +508,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 4 && (value == 128 || value == 256)) return ngnn_set_gemm_tile(value);
   if (key == 8 && value >= 0 && value <= 4096) return ngnn_set_wgrad_splits(value);
   if (key == 9 && value >= 0 && value <= 2) { g_tune_wide = value; return NGNN_OK; }
+  if (key == 10 && (value == 0 || value == 1)) { g_use_pdl = value; return NGNN_OK; }
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);

@@ -39,6 +39,26 @@ void count_launches(int n);
 
 static inline cudaStream_t as_stream(ngnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch.  The step is a chain of ~15 dependent kernels and each boundary costs a launch latency of a
+// few microseconds on top of the predecessor's tail.  A kernel launched with launch_chain() may be scheduled as soon as
+// every CTA of its predecessor in the stream has started (pdl_trigger at the top of each kernel) and then blocks in
+// pdl_wait() until the predecessor has completed and flushed — its CTAs are already resident when that happens.
+// Both instructions are no-ops for a kernel launched the ordinary way.  The attribute is OFF by default (measured slower on the
+// full step, see abi.cu); ngnn_set_tuning(10, 1) turns it on.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+extern int g_use_pdl;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }

@@ -62,7 +62,7 @@ int32_t prep_batch_add(int32_t mode, const float* w_l, const float* w_r, int64_t
 int32_t prep_batch_launch(cudaStream_t st) {
   const PrepBatch& b = t_prep_batch;
   if (b.n_jobs == 0) return NGNN_OK;
-  k_prep_weights_batch<<<(unsigned)b.first_block[b.n_jobs], 256, 0, st>>>(b);
+  launch_chain(k_prep_weights_batch, dim3((unsigned)b.first_block[b.n_jobs]), dim3(256), 0, st, b);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;
 }

@@ -196,6 +196,8 @@ struct ReduceJobs {
   int32_t n;
 };
 __global__ void k_reduce_partials_multi(const ReduceJobs jobs, int32_t splits, int32_t accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const ReduceJob jb = jobs.job[blockIdx.y];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= jb.n) return;

@@ -288,6 +288,8 @@ struct PrepBatch {
   int32_t n_jobs;
 };
 __global__ void k_prep_weights_batch(const __grid_constant__ PrepBatch b) {
+  pdl_trigger();
+  pdl_wait();
   int j = 0;
   while (j + 1 < b.n_jobs && (int32_t)blockIdx.x >= b.first_block[j + 1]) ++j;
   prep_weights_element(b.job[j], (int64_t)(blockIdx.x - b.first_block[j]) * blockDim.x + threadIdx.x);
@@ -348,6 +350,7 @@ template <bool TS>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
           const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcGemmParams p) {
+  pdl_trigger();       // the next kernel of the chain may be scheduled; it blocks in its own pdl_wait until this grid is done
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -367,10 +370,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t KB = p.kblocks1 + p.kblocks2;
-  int32_t M = p.M;
-  if (p.M_dev != nullptr) { const int32_t v = __ldg(p.M_dev); M = v < p.M ? (v < 0 ? 0 : v) : p.M; }
-  const int32_t m_tiles = (M + TC_BM - 1) / TC_BM;
-  const int32_t total_tiles = m_tiles * p.tiles_per_seg * p.num_segs;
+  int32_t M = p.M;                                     // (the device-side row count is read after pdl_wait below)
   uint32_t buf_cols = 32;
   while (buf_cols < (uint32_t)p.BN) buf_cols <<= 1;
   const uint32_t tmem_cols = TS ? 512u : 2 * buf_cols;
@@ -393,6 +393,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, tensor-memory allocation, descriptor prefetch) touched no data of the preceding kernel and
+  // ran under its tail; nothing below may start before it has completed
+  pdl_wait();
+  if (p.M_dev != nullptr) { const int32_t v = __ldg(p.M_dev); M = v < p.M ? (v < 0 ? 0 : v) : p.M; }
+  const int32_t m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int32_t total_tiles = m_tiles * p.tiles_per_seg * p.num_segs;
 
   // tile -> (m tile, segment, n tile): consecutive tiles walk M so that co-running CTAs share the same B tile in L2
   auto decode = [&](int32_t tile, int32_t& m0, int32_t& seg_id, int32_t& n0) {
@@ -706,8 +712,8 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
   pp.num_segs = num_segs;
   const int64_t tiles = ceil_div(p.M, TC_BM) * pl.tiles_per_seg * num_segs;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);      // persistent: one CTA per SM
-  if (pl.ts) k_tc_gemm<true><<<grid, TG_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, pp);
-  else k_tc_gemm<false><<<grid, TG_THREADS, pl.smem_bytes, st>>>(a1, a2, bh, bl, pp);
+  if (pl.ts) launch_chain(k_tc_gemm<true>, dim3(grid), dim3(TG_THREADS), pl.smem_bytes, st, a1, a2, bh, bl, pp);
+  else launch_chain(k_tc_gemm<false>, dim3(grid), dim3(TG_THREADS), pl.smem_bytes, st, a1, a2, bh, bl, pp);
   NGNN_LAUNCH_CHECK();
   return NGNN_OK;
 }
@@ -910,6 +916,8 @@ template <bool TS>
 __global__ void __launch_bounds__(TW_THREADS, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX1,
            const __grid_constant__ CUtensorMap tmX2, const TcWgradParams p) {
+  pdl_trigger();
+  pdl_wait();          // (n is read from device memory right below: nothing of the prologue can run ahead of the predecessor)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -1229,8 +1237,8 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(O, TC_BM), (unsigned)(pl.tiles_per_seg * ns), (unsigned)pl.splits);
-  if (pl.ts) k_tc_wgrad<true><<<grid, TW_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
-  else k_tc_wgrad<false><<<grid, TW_THREADS, pl.smem_bytes, st>>>(tDY, tX1, tX2, p);
+  if (pl.ts) launch_chain(k_tc_wgrad<true>, grid, dim3(TW_THREADS), pl.smem_bytes, st, tDY, tX1, tX2, p);
+  else launch_chain(k_tc_wgrad<false>, grid, dim3(TW_THREADS), pl.smem_bytes, st, tDY, tX1, tX2, p);
   NGNN_LAUNCH_CHECK();
   if (!direct) {
     // same per-element summation order as k_reduce_partials; both weight gradients and the bias gradient in one launch
@@ -1238,7 +1246,7 @@ static inline int32_t tc_gemm_wgrad(const float* dy, int64_t ld_dy, const float*
     for (int j = 0; j < ns; ++j) jobs.job[jobs.n++] = ReduceJob{parts[j], outs[j], O * F, O * F};
     if (fuse_db) jobs.job[jobs.n++] = ReduceJob{part_db, db, O, O};
     dim3 rgrid((unsigned)ceil_div(O * F, 256), (unsigned)jobs.n);
-    k_reduce_partials_multi<<<rgrid, 256, 0, st>>>(jobs, pl.splits, accumulate);
+    launch_chain(k_reduce_partials_multi, rgrid, dim3(256), 0, st, jobs, pl.splits, accumulate);
     NGNN_LAUNCH_CHECK();
     if (fuse_db && db_done) *db_done = true;
   }

@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) k_ce_rows_reduce(const float* __restrict_
                                                         const int32_t* __restrict__ row_ids, int64_t bs, int64_t C,
                                                         float grad_scale, float* rows, float* __restrict__ dlogits,
                                                         int64_t ld_d, StepCtl* ctl, float* stats) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_l[256], s_c[256];
   __shared__ int s_last;
   const float w = __uint_as_float(ctl->loss_scale_bits);
@@ -265,6 +267,8 @@ __global__ void __launch_bounds__(1024) k_ct_reduce(const float* __restrict__ sc
 __global__ void k_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                        float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
                        float weight_decay, float grad_scale, int64_t* step_dev, unsigned int* ticket) {
+  pdl_trigger();
+  pdl_wait();
   // the two bias corrections (double-precision pow) once per CTA, not once per parameter
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {
@@ -311,8 +315,8 @@ int32_t ce_impl(const float* logits, int64_t ld, const int64_t* target, const in
   NGNN_REQUIRE(logits && target && stats && row_scratch, NGNN_E_INVALID, "ce: null pointer");
   NGNN_REQUIRE(ld >= C && (dlogits == nullptr || ld_d >= C), NGNN_E_INVALID, "ce: leading dimension < C");
   if (ctl != nullptr) {      // replayed step: one launch, the last CTA reduces (ticket in the control words)
-    k_ce_rows_reduce<<<(unsigned)ceil_div(bs * 32, 256), 256, 0, st>>>(logits, ld, target, y_true, row_ids, bs, C, grad_scale,
-                                                                         row_scratch, dlogits, ld_d, const_cast<StepCtl*>(ctl), stats);
+    launch_chain(k_ce_rows_reduce, dim3((unsigned)ceil_div(bs * 32, 256)), dim3(256), 0, st, logits, ld, target, y_true, row_ids, bs, C,
+                 grad_scale, row_scratch, dlogits, ld_d, const_cast<StepCtl*>(ctl), stats);
     NGNN_LAUNCH_CHECK();
     return NGNN_OK;
   }
@@ -372,8 +376,8 @@ int32_t ngnn_adam_step(float* param, const float* grad, float* exp_avg, float* e
     NGNN_REQUIRE(param && grad && exp_avg && exp_avg_sq, NGNN_E_INVALID, "adam: null pointer");
     // advance_step == 2: step_dev[1] is a zero-initialised ticket word owned by this call sequence (no second launch)
     unsigned int* ticket = advance_step == 2 ? reinterpret_cast<unsigned int*>(step_dev + 1) : nullptr;
-    k_adam<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                       weight_decay, grad_scale, step_dev, ticket);
+    launch_chain(k_adam, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                 weight_decay, grad_scale, step_dev, ticket);
     NGNN_LAUNCH_CHECK();
     if (ticket != nullptr) return NGNN_OK;
   }
