@@ -271,21 +271,29 @@ def run_ours(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     import ctypes
-    Kp = min(K, 50)
+    Kp = min(K, 16)
     trainer.use_graph = False
     start = pos["next"]
     pos["next"] += W + Kp
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    def hold_gpu():
+        # Eager issue is host-bound (~0.45 ms of launches per step): an event recorded by a host that is NOT ahead of the GPU
+        # would time the host's gap between two enqueues, not the kernel.  A spin kernel holds the GPU for ~25 ms while the
+        # host queues all Kp steps; everything between the two events of a pair is then GPU-side.
+        torch.cuda._sleep(50_000_000)
+
     def probe_hook(j):
         if j == W - 1:
             barrier()
             _lib.call("ngnn_probe_enable", Kp)
+            hold_gpu()
             ev0.record()
         if j == W + Kp - 1:
             ev1.record()
     if W == 0:
         _lib.call("ngnn_probe_enable", Kp)
+        hold_gpu()
         ev0.record()
     trainer.run_steps(loader, W + Kp, start_epoch=start // spe, start_step=start % spe, seeds_resident=True,
                       log_every_step=False, on_step=probe_hook)
@@ -295,6 +303,8 @@ def run_ours(args):
     buf, cnt = (ctypes.c_float * Kp)(), ctypes.c_int32(0)
     _lib.call("ngnn_probe_read", buf, Kp, ctypes.byref(cnt))
     agg_ms = list(buf[:cnt.value])
+    _lib.call("ngnn_probe_read_device_clock", buf, Kp, ctypes.byref(cnt))
+    agg_ms_dev = [v for v in buf[:cnt.value] if v > 0]
     _lib.call("ngnn_probe_enable", 0)
     _, agg_bytes = region_blocks(start + W, Kp, want_bytes=True)
     achieved = (sum(agg_bytes) / len(agg_bytes)) / (sum(agg_ms) / len(agg_ms) * 1e-3) / 1e9 if agg_ms else None
@@ -304,10 +314,16 @@ def run_ours(args):
                 "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "avg_launch_us": 1e3 * sum(agg_ms) / len(agg_ms) if agg_ms else None,
+                # the same launches by the device's own clock (first CTA start -> last CTA end, %globaltimer): what the event
+                # pair adds on top is the two records and the launch latency
+                "avg_launch_us_device_clock": 1e3 * sum(agg_ms_dev) / len(agg_ms_dev) if agg_ms_dev else None,
+                "frac_device_clock": (sum(agg_bytes) / len(agg_bytes)) / (sum(agg_ms_dev) / len(agg_ms_dev) * 1e-3) / 1e9 / peak_gbs
+                if agg_ms_dev else None,
                 "algorithmic_bytes_per_launch": sum(agg_bytes) / len(agg_bytes) if agg_bytes else None,
                 "share_of_step": (sum(agg_ms) / len(agg_ms)) / (ms_total / K) if agg_ms else None,
-                "timing": f"CUDA events on the launching stream around this kernel's launch in {Kp} eagerly issued steps "
-                          f"({eager_ms / Kp:.3f} ms/step eager vs {ms_total / K:.3f} replayed); share_of_step is against the replayed step"}
+                "timing": f"CUDA events on the launching stream around this kernel's launch in {Kp} eagerly issued steps, queued "
+                          f"while a spin kernel holds the GPU so that the host is ahead ({eager_ms / Kp:.3f} ms/step vs "
+                          f"{ms_total / K:.3f} replayed); share_of_step is against the replayed step"}
 
     # ---- CPU baseline + parity check on the host cores (rank 0, N = 1 only) ----
     cpu_baseline = parity = None

@@ -35,6 +35,7 @@ struct AggParams {
   const float* bias;       // optional per-column bias added after the reduction (GCNConv: out = A_sum z + b)
   int32_t keep_l2;         // table-mode gathers (root_idx != NULL) carry an L2 priority:
   int64_t hot_rows;        //   < 0: every row evict_last; >= 0: rows < hot_rows evict_last, the others evict_first
+  unsigned long long* clock; // optional [2]: min %globaltimer at CTA start / max at CTA end (in-kernel duration, ngnn_probe_*)
   const int32_t* root_idx; // optional fused root gather (fwd): root[i] = x[root_idx[i]]
   float* root;
   int64_t ld_root;
@@ -279,10 +280,17 @@ __global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
 // runs a 3-stage pipeline in registers: while the feature rows of row i are in flight it has already issued
 // the index load of row i+1 and the extent / root-id loads of row i+2, so each iteration exposes ONE latency.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int VPL, int U, bool ROOT>
 __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
   pdl_trigger();
   pdl_wait();
+  if (p.clock != nullptr && threadIdx.x == 0) atomicMin(p.clock, global_ns());
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = agg_rows(p);
@@ -353,6 +361,10 @@ __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
     // rotate the pipeline registers
     row0 = row1; beg0 = beg1; end0 = end1; rid0 = rid1; my0 = my1;
     row1 = row2; beg1 = beg2; end1 = end2; rid1 = rid2;
+  }
+  if (p.clock != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(p.clock + 1, global_ns());
   }
 }
 
@@ -451,7 +463,7 @@ static int32_t run_agg(const AggParams& p, cudaStream_t st) {
 namespace ngnn {
 int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, Ext n_dst,
                            int64_t F, float* mean, int64_t ld_mean, const int32_t* root_table, float* root, int64_t ld_root,
-                           int64_t hot_rows, cudaStream_t st) {
+                           int64_t hot_rows, cudaStream_t st, unsigned long long* clock) {
   if (n_dst.cap == 0 || F == 0) return NGNN_OK;
   NGNN_REQUIRE(rowptr && table && mean && ld_table >= F && ld_mean >= F, NGNN_E_INVALID, "agg_fwd_table: bad arguments");
   // (Measured, round 1: reserving an L2 persisting set-aside for the hot rows — cudaLimitPersistingL2CacheSize — made this
@@ -460,7 +472,7 @@ int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, cons
   p.ptr = rowptr; p.idx = col_table; p.x = table; p.ld_x = ld_table; p.n_rows = n_dst.cap; p.n_rows_dev = n_dst.dev; p.F = F;
   p.out = mean; p.ld_out = ld_mean; p.mean = 1;
   p.root_idx = root_table; p.root = root; p.ld_root = ld_root;
-  p.keep_l2 = g_tune_keep; p.hot_rows = hot_rows;
+  p.keep_l2 = g_tune_keep; p.hot_rows = hot_rows; p.clock = clock;
   return run_agg(p, st);
 }
 

@@ -102,7 +102,7 @@ struct StepCtl {
 // L2 evict_last priority, the rest with evict_first (hot_rows < 0: every row evict_last).
 int32_t agg_fwd_table_impl(const int32_t* rowptr, const int32_t* col_table, const float* table, int64_t ld_table, Ext n_dst,
                            int64_t F, float* mean, int64_t ld_mean, const int32_t* root_table, float* root, int64_t ld_root,
-                           int64_t hot_rows, cudaStream_t st);
+                           int64_t hot_rows, cudaStream_t st, unsigned long long* clock = nullptr);
 int32_t agg_fwd_impl(const int32_t* rowptr, const int32_t* col, const float* x, int64_t ld_x, Ext n_dst, int64_t F, float* mean,
                      int64_t ld_mean, cudaStream_t st);
 int32_t agg_bwd_impl(const int32_t* colptr_t, const int32_t* row_t, const float* dmean_scaled, int64_t ld_dmean, Ext n_src,

@@ -128,6 +128,7 @@ static int32_t ensure_aux(AuxCtx** out) {
 // CUDA events recorded on the caller's stream around that one launch, a pair per step.
 static cudaEvent_t* g_probe_ev = nullptr;
 static int g_probe_cap = 0, g_probe_n = 0;
+static unsigned long long* g_probe_clk = nullptr;     // device [2 * cap]: (min start, max end) %globaltimer of each probed launch
 
 }  // namespace ngnn
 
@@ -138,10 +139,19 @@ extern "C" {
 int32_t ngnn_probe_enable(int32_t max_samples) {
   for (int i = 0; i < 2 * g_probe_cap; ++i) cudaEventDestroy(g_probe_ev[i]);
   delete[] g_probe_ev;
-  g_probe_ev = nullptr; g_probe_cap = 0; g_probe_n = 0;
+  if (g_probe_clk) cudaFree(g_probe_clk);
+  g_probe_ev = nullptr; g_probe_clk = nullptr; g_probe_cap = 0; g_probe_n = 0;
   if (max_samples <= 0) return NGNN_OK;
   g_probe_ev = new cudaEvent_t[2 * (size_t)max_samples];
   for (int i = 0; i < 2 * max_samples; ++i) NGNN_CUDA(cudaEventCreate(&g_probe_ev[i]));
+  {   // (a measurement facility: the one place the library allocates) start words = all ones, end words = 0
+    NGNN_CUDA(cudaMalloc(&g_probe_clk, 2 * (size_t)max_samples * sizeof(unsigned long long)));
+    unsigned long long* h = new unsigned long long[2 * (size_t)max_samples];
+    for (int i = 0; i < max_samples; ++i) { h[2 * i] = ~0ull; h[2 * i + 1] = 0ull; }
+    cudaError_t e = cudaMemcpy(g_probe_clk, h, 2 * (size_t)max_samples * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    delete[] h;
+    NGNN_CUDA(e);
+  }
   g_probe_cap = max_samples;
   return NGNN_OK;
 }
@@ -153,6 +163,22 @@ int32_t ngnn_probe_read(float* ms, int32_t cap, int32_t* n) {
     NGNN_CUDA(cudaEventSynchronize(g_probe_ev[2 * i + 1]));
     NGNN_CUDA(cudaEventElapsedTime(&ms[i], g_probe_ev[2 * i], g_probe_ev[2 * i + 1]));
   }
+  *n = m;
+  return NGNN_OK;
+}
+
+int32_t ngnn_probe_read_device_clock(float* ms, int32_t cap, int32_t* n) {
+  NGNN_REQUIRE(ms && n, NGNN_E_INVALID, "probe_read_device_clock: null pointer");
+  const int m = g_probe_n < cap ? g_probe_n : cap;
+  *n = 0;
+  if (m == 0 || g_probe_clk == nullptr) return NGNN_OK;
+  NGNN_CUDA(cudaDeviceSynchronize());
+  unsigned long long* h = new unsigned long long[2 * (size_t)m];
+  cudaError_t e = cudaMemcpy(h, g_probe_clk, 2 * (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess)
+    for (int i = 0; i < m; ++i) ms[i] = h[2 * i + 1] > h[2 * i] ? (float)((double)(h[2 * i + 1] - h[2 * i]) * 1e-6) : 0.f;
+  delete[] h;
+  NGNN_CUDA(e);
   *n = m;
   return NGNN_OK;
 }
@@ -214,7 +240,7 @@ static int32_t agg1_launch(const ngnn_block_t* block, const StepPlan& pl, const 
   const bool remapped = block->col_table != nullptr && block->n_table != nullptr;      // table stored hot rows first
   const int32_t rc = agg_fwd_table_impl(block->rowptr, remapped ? block->col_table : block->col_global, table, ld_table, n_dst, lp.F,
                                         mean, lp.ldf, remapped ? block->n_table : block->n_id, root, lp.ldf,
-                                        remapped ? block->hot_rows : -1, st);
+                                        remapped ? block->hot_rows : -1, st, probe && g_probe_clk ? g_probe_clk + 2 * g_probe_n : nullptr);
   if (probe) { cudaEventRecord(g_probe_ev[2 * g_probe_n + 1], st); ++g_probe_n; }
   return rc;
 }

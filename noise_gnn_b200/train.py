@@ -205,6 +205,7 @@ class Trainer:
             H = len(loader.num_neighbors)
             T = min(self._cfg["num_layers"] - 1, H, 4)
             gs = dict(key=key, loader=loader, tgt=tgt, lab=lab, ms=ms, arena=arena, table=table, H=H, T=T,
+                      capture_stream=torch.cuda.Stream(device=arena.device),
                       slots=loader.fixed_slots(2, T), side=torch.cuda.Stream(device=arena.device), graphs=[None, None],
                       graph_launches=[0, 0])
             self._gs = gs
@@ -332,7 +333,7 @@ class Trainer:
                     if gs["graphs"][k] is None:
                         c0 = lib.ngnn_launch_count()
                         g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
+                        with torch.cuda.graph(g, stream=gs["capture_stream"]):
                             self._enqueue_pair(gs, k, bs_full, bs_full)
                         gs["graphs"][k] = g
                         gs["graph_launches"][k] = int(lib.ngnn_launch_count() - c0)
