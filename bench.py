@@ -311,7 +311,10 @@ def run_ours(args):
     roofline = {"kernel": "K-AGG layer 1 (mean of sampled in-neighbours + root gather from the resident table)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs if achieved else None,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ONE ncu --set full capture of a step of this workload
+                # (profiles/r02_ncu_agg_pipe_raw.csv: 211.7 MB + 43.8 MB); a static figure, not re-measured by this run
+                "traffic": 255.5e6 if args.workload == "products" and args.scale == 1.0 else None,
+                "traffic_source": "static: profiles/r02_ncu_agg_pipe_raw.csv (ncu --set full, one launch)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "avg_launch_us": 1e3 * sum(agg_ms) / len(agg_ms) if agg_ms else None,
                 # the same launches by the device's own clock (first CTA start -> last CTA end, %globaltimer): what the event

@@ -35,6 +35,7 @@ struct AggParams {
   const float* bias;       // optional per-column bias added after the reduction (GCNConv: out = A_sum z + b)
   int32_t keep_l2;         // table-mode gathers (root_idx != NULL) carry an L2 priority:
   int64_t hot_rows;        //   < 0: every row evict_last; >= 0: rows < hot_rows evict_last, the others evict_first
+  int32_t long_row;        // rows with more neighbours than this are reduced by the whole CTA (hub rows)
   unsigned long long* clock; // optional [2]: min %globaltimer at CTA start / max at CTA end (in-kernel duration, ngnn_probe_*)
   const int32_t* root_idx; // optional fused root gather (fwd): root[i] = x[root_idx[i]]
   float* root;
@@ -112,7 +113,10 @@ __device__ __forceinline__ void seg_finish(const AggParams& p, int64_t row, int 
 // G == 32 only: rows longer than kLongRow (hubs of a power-law graph: un-sampled convolutions, the transposed blocks of
 // the backward) are not walked by their one warp — the CTA's warps each reduce a contiguous slice of the row and the
 // slices are combined through shared memory in warp order (still atomic-free and run-to-run deterministic).
-constexpr int kLongRow = 1024;
+// Measured on the Computers-shaped sweep (transposed rows: mean 10, p99 58, max 139 neighbours; profiles/prof_wide.py): lowering
+// the threshold from 1024 to 64 takes the F = 512 transpose-sum from 108 us to 80 us and F = 1024 from 219 us to 166 us — the
+// few rows an order of magnitude above the mean were each walked by one warp while the rest of the machine idled.
+constexpr int kLongRow = 64;
 constexpr int kLongWarps = 8;
 template <int G, int VPL>
 constexpr int seg_max_threads() { return (G == 16 && VPL == 4) ? 128 : 512; }   // the half-warp-per-row variant runs small CTAs
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(Agg
     beg = __ldg(p.ptr + row); end = __ldg(p.ptr + row + 1);
     if (gl == 0 && (int64_t)beg + kPrefetchRows < e_total) prefetch_l2(p.idx + beg + kPrefetchRows);
   }
-  const bool is_long = COOP && valid && (end - beg) > kLongRow;
+  const bool is_long = COOP && valid && (end - beg) > p.long_row;
   if (valid && !is_long) {
     const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
     const bool has_add = p.add != nullptr && row < agg_n_add(p);
@@ -389,6 +393,7 @@ static int g_tune_threads = 256; // ngnn_set_tuning(1, t): CTA size 128 / 256 / 
 static int g_tune_pipe = 1;      // ngnn_set_tuning(3, 0/1): software-pipelined persistent forward kernel
 static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 < F <= 128 (32 / 16 / 8)
 static int g_tune_keep = 1;      // ngnn_set_tuning(7, 0|1): L2 evict_last priority on the layer-1 table gathers
+static int g_tune_long = kLongRow;  // ngnn_set_tuning(11, n): hub-row threshold of the generic kernel
 static int g_tune_wide = 0;      // ngnn_set_tuning(9, v): generic kernel for 128 < F <= 256: 0 = half-warp/row x4 vectors, 128-thread
                                  //   CTAs (default); 1 = warp/row x2 vectors unroll 2; 2 = warp/row unroll 4
 
@@ -400,7 +405,9 @@ static void launch_v4(const AggParams& p, cudaStream_t st, int threads = 0) {
   launch_chain(k_seg_reduce_v4<G, VPL, U>, dim3((unsigned)ceil_div(p.n_rows, rows_per_block)), dim3(T), 0, st, p);
 }
 
-static int32_t run_agg(const AggParams& p, cudaStream_t st) {
+static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
+  AggParams p = p_in;
+  p.long_row = g_tune_long;
   if (p.n_rows == 0 || p.F == 0) return NGNN_OK;
   // 128-bit path: rows addressed as whole float4 vectors.  A width that is not a multiple of 4 (1433, 767) qualifies when
   // every row has the padding behind it (ld >= 4*ceil(F/4), as the loader's table and the step arena guarantee): the last
@@ -521,6 +528,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 8 && value >= 0 && value <= 4096) return ngnn_set_wgrad_splits(value);
   if (key == 9 && value >= 0 && value <= 2) { g_tune_wide = value; return NGNN_OK; }
   if (key == 10 && (value == 0 || value == 1)) { g_use_pdl = value; return NGNN_OK; }
+  if (key == 11 && value >= 32 && value <= (1 << 20)) { g_tune_long = value; return NGNN_OK; }
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }
   return ngnn::set_error(NGNN_E_INVALID, "set_tuning: unknown key/value %d/%d", key, value);

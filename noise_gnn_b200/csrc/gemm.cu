@@ -88,13 +88,13 @@ int32_t gemm_fwd_impl(const float* a_l, int64_t ld_al, const float* a_r, int64_t
     if (rc == NGNN_OK) { if (path) *path = 1; return NGNN_OK; }
     if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
-  NGNN_REQUIRE(n_dev == nullptr && ctl == nullptr && !concat_k, NGNN_E_UNSUPPORTED,
-               "gemm_fwd: device-side extents need TMA-addressable operands (16-byte aligned bases, ld %% 4 == 0)");
+  NGNN_REQUIRE(!concat_k, NGNN_E_UNSUPPORTED, "gemm_fwd: the one-contraction form needs the tensor-core path");
 
   SimtGemmParams p{};
   if (a_l) { p.A1 = {a_l, ld_al, 1}; p.B1 = {w_l, F, 1}; p.K1 = F; }
   if (a_r) { p.A2 = {a_r, ld_ar, 1}; p.B2 = {w_r, F, 1}; p.K2 = F; }
   p.M = n; p.N = O; p.C = out; p.ldc = ld_out; p.bias = bias; p.act = act; p.drop_p = drop_p;
+  p.M_dev = n_dev; p.ctl = ctl; p.ctl_layer = ctl_layer;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
   p.off_lo = (uint32_t)offset; p.off_hi = (uint32_t)(offset >> 32);
   return launch_simt_gemm(p, 1, st);
@@ -114,18 +114,17 @@ int32_t dgrad_impl(const float* dy, int64_t ld_dy, const float* w_l, const float
                                ws_bytes, st, prepped, n_dev);
     if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
-  NGNN_REQUIRE(n_dev == nullptr, NGNN_E_UNSUPPORTED, "dgrad: device-side extents need TMA-addressable operands");
   if (dmean_scaled) {
     SimtGemmParams p{};
     p.A1 = {dy, ld_dy, 1}; p.B1 = {w_l, 1, F}; p.K1 = O;
-    p.M = n; p.N = F; p.C = dmean_scaled; p.ldc = ld_dmean; p.rowptr_scale = rowptr;
+    p.M = n; p.M_dev = n_dev; p.N = F; p.C = dmean_scaled; p.ldc = ld_dmean; p.rowptr_scale = rowptr;
     int32_t rc = launch_simt_gemm(p, 1, st);
     if (rc != NGNN_OK) return rc;
   }
   if (dx_root) {
     SimtGemmParams p{};
     p.A1 = {dy, ld_dy, 1}; p.B1 = {w_r, 1, F}; p.K1 = O;
-    p.M = n; p.N = F; p.C = dx_root; p.ldc = ld_root;
+    p.M = n; p.M_dev = n_dev; p.N = F; p.C = dx_root; p.ldc = ld_root;
     int32_t rc = launch_simt_gemm(p, 1, st);
     if (rc != NGNN_OK) return rc;
   }
@@ -166,7 +165,6 @@ int32_t wgrad_impl(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_
     else if (rc != NGNN_E_UNSUPPORTED) return rc;
   }
   if (!done && (dw_l || dw_r)) {
-    NGNN_REQUIRE(n_dev == nullptr, NGNN_E_UNSUPPORTED, "wgrad: device-side extents need TMA-addressable operands");
     const int32_t S = wgrad_splits(n, F, O);
     const float* as[2] = {a_l, a_r};
     const int64_t lds[2] = {ld_al, ld_ar};
@@ -174,7 +172,7 @@ int32_t wgrad_impl(const float* dy, int64_t ld_dy, const float* a_l, int64_t ld_
     for (int w = 0; w < 2; ++w) {
       if (!dws[w] || F == 0) continue;
       SimtGemmParams p{};
-      p.A1 = {dy, 1, ld_dy}; p.B1 = {as[w], 1, lds[w]}; p.K1 = n;
+      p.A1 = {dy, 1, ld_dy}; p.B1 = {as[w], 1, lds[w]}; p.K1 = n; p.K1_dev = n_dev;
       p.M = O; p.N = F; p.ldc = F;
       if (S == 1 && !accumulate) {
         p.C = dws[w]; p.split_stride = 0;

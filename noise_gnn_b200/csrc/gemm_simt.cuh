@@ -29,6 +29,10 @@ struct SimtGemmParams {
   float drop_p;              // 0 => no dropout
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
   const int32_t* rowptr_scale;  // optional: row m scaled by 1/max(rowptr[m+1]-rowptr[m],1)
+  const int32_t* M_dev;         // optional device-side row count (clamped to M: the grid is sized for M)
+  const int32_t* K1_dev;        // optional device-side length of the first contraction (weight gradients: the block's rows)
+  const StepCtl* ctl;           // optional device-side step control: dropout offset = ctl->drop_off + ctl_layer
+  uint32_t ctl_layer;
 };
 
 // Keep-mask of the fused inverted dropout.  One Philox4x32-10 call (128 random bits) serves the 8 columns
@@ -94,7 +98,10 @@ __global__ void __launch_bounds__(SG_T) k_gemm_simt(SimtGemmParams p) {
   const int ty = t >> 4, tx = t & 15;
   const int64_t m0 = (int64_t)blockIdx.x * SG_BM, n0 = (int64_t)blockIdx.y * SG_BN;
 
-  const int32_t T1 = p.A1.p ? (int32_t)((p.K1 + SG_BK - 1) / SG_BK) : 0;
+  int64_t M = p.M, K1 = p.K1;
+  if (p.M_dev != nullptr) { const int64_t v = __ldg(p.M_dev); M = v < M ? (v < 0 ? 0 : v) : M; }
+  if (p.K1_dev != nullptr) { const int64_t v = __ldg(p.K1_dev); K1 = v < K1 ? (v < 0 ? 0 : v) : K1; }
+  const int32_t T1 = p.A1.p ? (int32_t)((K1 + SG_BK - 1) / SG_BK) : 0;
   const int32_t T2 = p.A2.p ? (int32_t)((p.K2 + SG_BK - 1) / SG_BK) : 0;
   const int32_t t_beg = blockIdx.z * p.tiles_per_split;
   const int32_t t_end = min(T1 + T2, t_beg + p.tiles_per_split);
@@ -108,10 +115,10 @@ __global__ void __launch_bounds__(SG_T) k_gemm_simt(SimtGemmParams p) {
   float ra[4], rb[4];
   auto fetch = [&](int32_t tile) {
     if (tile < T1) {
-      simt_load_tile(p.A1, m0, p.M, (int64_t)tile * SG_BK, p.K1, ra);
-      simt_load_tile(p.B1, n0, p.N, (int64_t)tile * SG_BK, p.K1, rb);
+      simt_load_tile(p.A1, m0, M, (int64_t)tile * SG_BK, K1, ra);
+      simt_load_tile(p.B1, n0, p.N, (int64_t)tile * SG_BK, K1, rb);
     } else {
-      simt_load_tile(p.A2, m0, p.M, (int64_t)(tile - T1) * SG_BK, p.K2, ra);
+      simt_load_tile(p.A2, m0, M, (int64_t)(tile - T1) * SG_BK, p.K2, ra);
       simt_load_tile(p.B2, n0, p.N, (int64_t)(tile - T1) * SG_BK, p.K2, rb);
     }
   };
@@ -142,16 +149,21 @@ __global__ void __launch_bounds__(SG_T) k_gemm_simt(SimtGemmParams p) {
   float* C = p.C + (int64_t)blockIdx.z * p.split_stride;
   const uint32_t thr = dropout_threshold(p.drop_p);
   const float keep_scale = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+  uint32_t off_lo = p.off_lo, off_hi = p.off_hi;
+  if (p.ctl != nullptr) {
+    const uint64_t o = (((uint64_t)p.ctl->drop_off_hi << 32) | p.ctl->drop_off_lo) + p.ctl_layer;
+    off_lo = (uint32_t)o; off_hi = (uint32_t)(o >> 32);
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t m = m0 + ty * 4 + i;
-    if (m >= p.M) continue;
+    if (m >= M) continue;
     float rs = 1.0f;
     if (p.rowptr_scale) rs = 1.0f / (float)max(__ldg(p.rowptr_scale + m + 1) - __ldg(p.rowptr_scale + m), 1);
     const int64_t nb = n0 + tx * 4;
     uint32_t keep = 0xFu;
     if (p.drop_p > 0.f && nb < p.N)
-      keep = dropout_keep4((uint32_t)m, (uint32_t)(nb >> 2), p.seed_lo, p.seed_hi, p.off_lo, p.off_hi, thr);
+      keep = dropout_keep4((uint32_t)m, (uint32_t)(nb >> 2), p.seed_lo, p.seed_hi, off_lo, off_hi, thr);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t n = nb + j;
