@@ -309,7 +309,9 @@ struct TcGemmParams {
   const StepCtl* ctl;         // optional device-side step control: dropout offset = ctl->drop_off + ctl_layer
   uint32_t ctl_layer;
   int32_t BN;                 // UMMA N / columns per CTA tile
-  int32_t kblocks1, kblocks2; // K-blocks of operand pair 1 / 2
+  int32_t kblocks1, kblocks2; // K-blocks of operand pair 1 / 2 covered by THIS launch
+  int32_t kb_begin1, kb_begin2; // first K-block of each pair this launch covers (a long contraction is cut into several launches)
+  int32_t acc_in, final;      // acc_in: add the output the previous launch left; final: apply bias / scale / activation / dropout
   int32_t b_koff2;            // k offset (floats) of pair 2 in the packed B planes
   int32_t stages;
   int32_t tiles_per_seg;      // N tiles per segment
@@ -422,7 +424,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
           const uint32_t ph = si.ph;
           uint8_t* st = smem + (size_t)s * stage_bytes;
           const bool first = kb < p.kblocks1;
-          const int32_t ka = (first ? kb : kb - p.kblocks1) * TC_BK;
+          const int32_t ka = (first ? kb + p.kb_begin1 : kb - p.kblocks1 + p.kb_begin2) * TC_BK;
           const int32_t kbk = first ? ka : p.b_koff2 + ka;
           // TS: the raw A slot is free as soon as the converters have copied it to registers — about one MMA period before
           // the stage's MMAs retire — so the A tile (the one with a conversion step behind it) is requested that much earlier:
@@ -595,21 +597,33 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
           }
           if (!live) continue;
           uint32_t keep16 = 0xFFFFu;                              // nb is a multiple of 16: two 8-column Philox groups
-          if (p.drop_p > 0.f && row_ok) {
+          if (p.drop_p > 0.f && row_ok && p.final) {
             keep16 = dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3), p.seed_lo, p.seed_hi, off_lo, off_hi, thr);
             if (nb + 8 < sg.n_cols)
               keep16 |= dropout_keep8((uint32_t)m, (uint32_t)(nb >> 3) + 1u, p.seed_lo, p.seed_hi, off_lo, off_hi, thr) << 8;
           }
           float r[16];
+          if (p.acc_in) {
+            // a contraction longer than one tensor-memory accumulation chain: this launch continues the partial result the
+            // previous one stored (each lane owns a row: 16 consecutive floats)
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const float prev = (row_ok && nb + jj < sg.n_cols) ? sg.out[m * sg.ld_out + nb + jj] : 0.f;
+              v[jj] = __float_as_uint(__uint_as_float(v[jj]) + prev);
+            }
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + 4 * g);     // smem broadcast
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              float x = (__uint_as_float(v[4 * g + jj]) + bb[jj]) * rs;
-              if (p.act == NGNN_ACT_RELU) x = fmaxf(x, 0.f);
-              if (p.drop_p > 0.f) x = ((keep16 >> (4 * g + jj)) & 1u) ? x * keep_scale : 0.f;
+              float x = __uint_as_float(v[4 * g + jj]);
+              if (p.final) {
+                x = (x + bb[jj]) * rs;
+                if (p.act == NGNN_ACT_RELU) x = fmaxf(x, 0.f);
+                if (p.drop_p > 0.f) x = ((keep16 >> (4 * g + jj)) & 1u) ? x * keep_scale : 0.f;
+              }
               r[4 * g + jj] = x;
             }
           }
@@ -723,15 +737,17 @@ static inline int32_t tc_launch(const CUtensorMap& a1, const CUtensorMap& a2, co
 // Packed hi / lo weight planes of the forward projection ([W_l | W_r], K-major) into ws.  `use_l` / `use_r`: which operand
 // pairs the GEMM will contract (a missing one is zero-filled).
 // A tensor-memory accumulation chain longer than this many K-blocks (x 12 MMAs, each rounding the accumulator toward zero)
-// drifts past the 1e-5 bar (see the K-WGRAD notes below): wider contractions take the SIMT kernel.
+// drifts past the 1e-5 bar (see the K-WGRAD notes below): a wider forward contraction is cut into several launches of at most
+// TC_CHAIN_KBLOCKS, each adding the output of the one before (fp32, round to nearest) — F = 767 / 1433 stay on the tensor cores.
 constexpr int TC_MAX_CHAIN_KBLOCKS = 40;
+constexpr int TC_CHAIN_KBLOCKS = 32;
 
 // concat_k: the two operands are the halves of ONE [n, 2F] matrix ([mean | root] side by side, layer 1 of the fused step), so the
 // weights are packed [W_l | W_r] without padding in between and the contraction runs over ceil(2F / 32) K-blocks instead of
 // 2 * ceil(F / 32) (F = 100: 7 instead of 8).
 static inline int32_t tc_prep_fwd(const float* w_l, const float* w_r, bool use_l, bool use_r, int64_t F, int64_t O, void* ws,
                                   size_t ws_bytes, cudaStream_t st, PrepParams* collect = nullptr, bool concat_k = false) {
-  if (F < 1 || O < 1 || 2 * ceil_div(F, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
+  if (F < 1 || O < 1) return NGNN_E_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_fwd_ws_bytes(F, O)) return NGNN_E_UNSUPPORTED;
   const int32_t Fpad = concat_k ? (int32_t)F : round_up_i(F, TC_BK), Kpack = concat_k ? round_up_i(2 * F, TC_BK) : 2 * Fpad;
   float* hi = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 256));
@@ -753,7 +769,6 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
                                   const StepCtl* ctl = nullptr, uint32_t ctl_layer = 0, bool concat_k = false) {
   if (F < 1 || n < 1 || O < 1 || n >= (1LL << 31) - 256) return NGNN_E_UNSUPPORTED;
   if (concat_k && !(a_l && a_r && a_r == a_l + F && ld_al == ld_ar && ld_al >= 2 * F)) return NGNN_E_UNSUPPORTED;
-  if (2 * ceil_div(F, TC_BK) > TC_MAX_CHAIN_KBLOCKS) return NGNN_E_UNSUPPORTED;
   if (a_l && !tma_addressable(a_l, ld_al)) return NGNN_E_UNSUPPORTED;
   if (a_r && !tma_addressable(a_r, ld_ar)) return NGNN_E_UNSUPPORTED;
   if (!a_l && !a_r) return NGNN_E_UNSUPPORTED;
@@ -787,16 +802,32 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
   p.seg[0] = TcSegment{out, ld_out, (int32_t)O, 0, 0};
   p.bias = bias; p.act = act; p.drop_p = drop_p;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.off_lo = (uint32_t)offset; p.off_hi = (uint32_t)(offset >> 32);
+  CUtensorMap shifted, shifted_lo;
+  const CUtensorMap* mBh = &tBh;
+  const CUtensorMap* mBl = &tBl;
   if (!a_l) {
     // only the root term: read its weights from k offset Fpad of the pack
-    CUtensorMap shifted;
+    p.b_koff2 = 0;
     ok = make_tmap_2d(&shifted, hi + Fpad, O, Fpad, Kpack, (uint32_t)pl.BN);
-    CUtensorMap shifted_lo;
     ok = ok && make_tmap_2d(&shifted_lo, lo + Fpad, O, Fpad, Kpack, (uint32_t)pl.BN);
     NGNN_REQUIRE(ok, NGNN_E_CUDA, "gemm_fwd: cuTensorMapEncodeTiled failed");
-    return tc_launch(tA1, tA2, shifted, shifted_lo, p, pl, 1, st);
+    mBh = &shifted; mBl = &shifted_lo;
   }
-  return tc_launch(tA1, tA2, tBh, tBl, p, pl, 1, st);
+  // one launch per accumulation chain of at most TC_CHAIN_KBLOCKS K-blocks (a single launch for every F <= 512)
+  const int32_t kb1 = p.kblocks1, kb2 = p.kblocks2, total = kb1 + kb2;
+  const int32_t chains = (total + TC_MAX_CHAIN_KBLOCKS - 1) / TC_MAX_CHAIN_KBLOCKS <= 1 ? 1 : (total + TC_CHAIN_KBLOCKS - 1) / TC_CHAIN_KBLOCKS;
+  const int32_t per = (total + chains - 1) / chains;
+  for (int32_t c = 0; c < chains; ++c) {
+    const int32_t g0 = c * per, g1 = g0 + per < total ? g0 + per : total;       // global K-block range of this launch
+    const int32_t o1b = g0 < kb1 ? g0 : kb1, o1e = g1 < kb1 ? g1 : kb1;         // part in operand 1
+    const int32_t b0 = g0 > kb1 ? g0 - kb1 : 0, b1 = g1 > kb1 ? g1 - kb1 : 0;   // part in operand 2
+    TcGemmParams pc = p;
+    pc.kblocks1 = o1e - o1b; pc.kb_begin1 = o1b; pc.kblocks2 = b1 - b0; pc.kb_begin2 = b0;
+    pc.acc_in = c > 0; pc.final = c == chains - 1;
+    const int32_t rc = tc_launch(tA1, tA2, *mBh, *mBl, pc, pl, 1, st);
+    if (rc != NGNN_OK) return rc;
+  }
+  return NGNN_OK;
 }
 
 // dmean_scaled = rowscale * (dy W_l), dx_root = dy W_r, both in one launch (two N segments).
@@ -847,7 +878,7 @@ static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float*
 
   TcGemmParams p{};
   p.M = (int32_t)n; p.M_dev = n_dev; p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
-  p.kblocks1 = Kpack / TC_BK; p.kblocks2 = 0; p.b_koff2 = 0;
+  p.kblocks1 = Kpack / TC_BK; p.kblocks2 = 0; p.b_koff2 = 0; p.final = 1;
   p.rowptr = rowptr;
   int ns = 0;
   if (dmean) p.seg[ns++] = TcSegment{dmean, ld_dmean, (int32_t)F, 0, rowptr != nullptr ? 1 : 0};

@@ -80,6 +80,47 @@ def test_gemm_fwd_many_tiles_per_cta(dev, gemm_path, n, F, O):
     assert torch.equal(got, ops.gemm_fwd(*d, n))
 
 
+def _pad4(t):
+    """The same values in storage whose row stride is a multiple of 4 floats (what the loader's feature table and the
+    step's activation arena use): TMA needs 16-byte row strides."""
+    n, F = t.shape
+    buf = torch.zeros(n, (F + 3) // 4 * 4, dtype=t.dtype, device=t.device)
+    buf[:, :F] = t
+    return buf[:, :F]
+
+
+# F % 4 != 0 and contractions longer than one tensor-memory accumulation chain (F = 1433 is cora, 767 computers, 500 pubmed):
+# with padded row strides these run on the tensor cores, a long contraction as several chained launches
+LONG_K = [(2708, 1433, 7), (3000, 767, 10), (5000, 1433, 256), (4000, 500, 3), (1000, 2047, 64), (700, 641, 512)]
+
+
+@pytest.mark.parametrize("n,F,O", LONG_K)
+def test_gemm_fwd_long_or_ragged_k_on_tensor_cores(dev, n, F, O):
+    from noise_gnn_b200 import ops
+    g = torch.Generator().manual_seed(n + F + O)
+    a_l, a_r = torch.randn(n, F, generator=g), torch.randn(n, F, generator=g)
+    w_l, w_r = torch.randn(O, F, generator=g) / F ** 0.5, torch.randn(O, F, generator=g) / F ** 0.5
+    b = torch.randn(O, generator=g)
+    want = a_l.double() @ w_l.double().T + a_r.double() @ w_r.double().T + b.double()
+    bound = a_l.double().abs() @ w_l.double().abs().T + a_r.double().abs() @ w_r.double().abs().T + b.double().abs()
+    d = [_pad4(a_l.to(dev)), _pad4(a_r.to(dev)), w_l.to(dev), w_r.to(dev), b.to(dev)]
+    got, path = ops.gemm_fwd(*d, n, return_path=True)
+    assert path == 1
+    assert rel_err(got, want) < RTOL and dot_err(got, want, bound) < RTOL
+    p = 0.5
+    got_d, path = ops.gemm_fwd(*d, n, act=1, drop_p=p, seed=1232, offset=9, return_path=True)
+    assert path == 1
+    keep = torch.from_numpy(philox.dropout_keep_mask(n, O, p, seed=1232, offset=9))
+    want_d = torch.where(keep, want.clamp(min=0) / (1 - p), torch.zeros_like(want))
+    clear = want.abs() > 1e-5 * bound
+    assert torch.equal((got_d != 0).cpu()[clear], (want_d != 0)[clear])
+    assert dot_err(got_d, want_d, bound / (1 - p)) < RTOL
+    # root-only (one operand), no bias
+    got_r, path = ops.gemm_fwd(None, d[1], None, d[3], None, n, return_path=True)
+    assert path == 1 and rel_err(got_r, a_r.double() @ w_r.double().T) < RTOL
+    assert torch.equal(got, ops.gemm_fwd(*d, n))
+
+
 @pytest.mark.parametrize("n,F,O", BIG_GEMMS)
 def test_dgrad_wgrad_many_tiles_per_cta(dev, gemm_path, n, F, O):
     from noise_gnn_b200 import ops
