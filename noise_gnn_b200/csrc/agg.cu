@@ -35,6 +35,7 @@ struct AggParams {
   const float* bias;       // optional per-column bias added after the reduction (GCNConv: out = A_sum z + b)
   int32_t keep_l2;         // table-mode gathers (root_idx != NULL) carry an L2 priority:
   int64_t hot_rows;        //   < 0: every row evict_last; >= 0: rows < hot_rows evict_last, the others evict_first
+  int32_t l1_alloc;        // gathers allocate in L1 (wide rows re-gathered by neighbouring output rows)
   int32_t long_row;        // rows with more neighbours than this are reduced by the whole CTA (hub rows)
   unsigned long long* clock; // optional [2]: min %globaltimer at CTA start / max at CTA end (in-kernel duration, ngnn_probe_*)
   const int32_t* root_idx; // optional fused root gather (fwd): root[i] = x[root_idx[i]]
@@ -73,7 +74,7 @@ __device__ __forceinline__ void seg_accumulate(const AggParams& p, int beg, int 
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           const int c = c0 + gl + v * G;
-          v4[u][v] = (c < F4 && j + u < cnt) ? ldg_nc_f4(src + c) : zero4;
+          v4[u][v] = (c < F4 && j + u < cnt) ? (p.l1_alloc ? __ldg(src + c) : ldg_nc_f4(src + c)) : zero4;
         }
       }
 #pragma unroll
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(Agg
   if (valid && !is_long) {
     const float scale = p.mean ? 1.0f / (float)max(end - beg, 1) : 1.0f;
     const bool has_add = p.add != nullptr && row < agg_n_add(p);
-    for (int c0 = 0; c0 < F4; c0 += G * VPL) {
+    for (int c0 = blockIdx.y * (G * VPL); c0 < F4; c0 += gridDim.y * (G * VPL)) {
       float4 acc[VPL];
 #pragma unroll
       for (int v = 0; v < VPL; ++v) acc[v] = zero4;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(Agg
       const int sb = min(lend, lbeg + wib * slice), se = wib < nw ? min(lend, sb + slice) : sb;
       const float scale = p.mean ? 1.0f / (float)max(lend - lbeg, 1) : 1.0f;
       const bool has_add = p.add != nullptr && lrow < agg_n_add(p);
-      for (int c0 = 0; c0 < F4; c0 += 32 * CV) {
+      for (int c0 = blockIdx.y * (32 * CV); c0 < F4; c0 += gridDim.y * (32 * CV)) {
         float4 acc[CV];
 #pragma unroll
         for (int v = 0; v < CV; ++v) acc[v] = zero4;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(Agg
     }
     if (!valid) return;
   }
-  if (p.root_idx != nullptr) {
+  if (p.root_idx != nullptr && blockIdx.y == 0) {
     const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)__ldg(p.root_idx + row) * p.ld_x);
     float4* dst = reinterpret_cast<float4*>(p.root + row * p.ld_root);
     for (int c = gl; c < F4; c += G) dst[c] = ldg_nc_f4(src + c);
@@ -394,20 +395,26 @@ static int g_tune_pipe = 1;      // ngnn_set_tuning(3, 0/1): software-pipelined 
 static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 < F <= 128 (32 / 16 / 8)
 static int g_tune_keep = 1;      // ngnn_set_tuning(7, 0|1): L2 evict_last priority on the layer-1 table gathers
 static int g_tune_long = kLongRow;  // ngnn_set_tuning(11, n): hub-row threshold of the generic kernel
+static int g_tune_xwide = 0;     // ngnn_set_tuning(12, v): F > 256: 0 = column chunks on grid.y (default); 1 = the row's warp walks them; 2 = 128-thread CTAs
+static int g_tune_l1 = 0;        // ngnn_set_tuning(13, v): gathers of the generic kernel allocate in L1: 0 = wide rows only, 1 = always, 2 = never
 static int g_tune_wide = 0;      // ngnn_set_tuning(9, v): generic kernel for 128 < F <= 256: 0 = half-warp/row x4 vectors, 128-thread
                                  //   CTAs (default); 1 = warp/row x2 vectors unroll 2; 2 = warp/row unroll 4
 
+// split_cols: the column chunks (G*VPL vectors each) of a wide row go to different CTAs (grid.y) instead of being walked
+// one after the other by the row's warp — more, smaller units of work and more rows in flight.
 template <int G, int VPL, int U>
-static void launch_v4(const AggParams& p, cudaStream_t st, int threads = 0) {
+static void launch_v4(const AggParams& p, cudaStream_t st, int threads = 0, bool split_cols = false) {
   int T = threads > 0 && g_tune_threads == 256 ? threads : g_tune_threads;
   if (T > seg_max_threads<G, VPL>()) T = seg_max_threads<G, VPL>();
   const int64_t rows_per_block = (T / 32) * (32 / G);
-  launch_chain(k_seg_reduce_v4<G, VPL, U>, dim3((unsigned)ceil_div(p.n_rows, rows_per_block)), dim3(T), 0, st, p);
+  const unsigned chunks = split_cols ? (unsigned)ceil_div((p.F + 3) / 4, (int64_t)G * VPL) : 1u;
+  launch_chain(k_seg_reduce_v4<G, VPL, U>, dim3((unsigned)ceil_div(p.n_rows, rows_per_block), chunks), dim3(T), 0, st, p);
 }
 
 static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
   AggParams p = p_in;
   p.long_row = g_tune_long;
+  p.l1_alloc = g_tune_l1 == 1 || (g_tune_l1 == 0 && p.F > 256);
   if (p.n_rows == 0 || p.F == 0) return NGNN_OK;
   // 128-bit path: rows addressed as whole float4 vectors.  A width that is not a multiple of 4 (1433, 767) qualifies when
   // every row has the padding behind it (ld >= 4*ceil(F/4), as the loader's table and the step arena guarantee): the last
@@ -454,8 +461,16 @@ static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
       else if (g_tune_wide == 1) launch_v4<32, 2, 2>(p, st);
       else launch_v4<16, 4, 2>(p, st, 128);
     }
-    else if (F4 <= 128) launch_v4<32, 4, 2>(p, st);
-    else launch_v4<32, 8, 1>(p, st);
+    else {
+      // F > 256 (profiles/prof_wide.py, Computers-shaped sweep): each 128-vector column chunk of a row goes to its own CTA
+      // row (grid.y), 4 vectors per lane x 2 neighbour rows in flight, gathers allocating in L1.  Against the row's warp
+      // walking its chunks with 8 vectors per lane (128 registers, 2 CTAs per SM): F = 1433, fan-out 25 forward 258 -> 129 us,
+      // transpose-sum 516 -> 190 us; F = 512 55 -> 49 / 106 -> 82 us.  Narrower chunks (1-2 vectors per lane) re-read the
+      // indices too often and were slower than no split; 1 or 4 rows in flight, 512-thread CTAs and the scalar kernel too.
+      if (g_tune_xwide == 1) launch_v4<32, 8, 1>(p, st);                        // round-1 form, kept for A/B
+      else if (g_tune_xwide == 2) launch_v4<32, 4, 2>(p, st, 128, true);
+      else launch_v4<32, 4, 2>(p, st, 0, true);
+    }
   } else {
     const unsigned grid = (unsigned)ceil_div(p.n_rows * 32, 256);
     if (p.F <= 128) k_seg_reduce_scalar<4><<<grid, 256, 0, st>>>(p);
@@ -528,6 +543,8 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 8 && value >= 0 && value <= 4096) return ngnn_set_wgrad_splits(value);
   if (key == 9 && value >= 0 && value <= 2) { g_tune_wide = value; return NGNN_OK; }
   if (key == 10 && (value == 0 || value == 1)) { g_use_pdl = value; return NGNN_OK; }
+  if (key == 12 && value >= 0 && value <= 2) { g_tune_xwide = value; return NGNN_OK; }
+  if (key == 13 && value >= 0 && value <= 2) { g_tune_l1 = value; return NGNN_OK; }
   if (key == 11 && value >= 32 && value <= (1 << 20)) { g_tune_long = value; return NGNN_OK; }
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }

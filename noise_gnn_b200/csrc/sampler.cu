@@ -9,7 +9,7 @@
 // B200-first design: the graph (CSC), the feature table and two N-sized relabel maps stay resident in HBM; a block is
 // built by a FIXED sequence of 5 + 2H launches with worst-case grids whose real extents live in device memory
 // (`counts`), so sampling needs no host round trip and is captured in the step's CUDA graph.  Per hop:
-//   k_hop_draw    count -> exclusive scan -> draw, ONE kernel: each CTA counts the picks of its 256 frontier nodes, publishes
+//   k_hop_draw    count -> exclusive scan -> draw, ONE kernel: each CTA counts the picks of its 64 frontier nodes, publishes
 //                 the tile total, sums the totals of the tiles before it (they are published before anything is waited
 //                 for, so there is no serial chain) and draws — one warp per node, lane = draw (Floyd's algorithm run
 //                 cooperatively in registers, then every lane fetches its neighbour at once).

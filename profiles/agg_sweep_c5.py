@@ -19,17 +19,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from noise_gnn_b200 import NeighborLoader, ops  # noqa: E402
+from noise_gnn_b200 import NeighborLoader, _lib, ops  # noqa: E402
 from noise_gnn_b200.synthetic import make_dataset  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=7)
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "agg_sweep_c5.json"))
 ap.add_argument("--no-products", action="store_true")
+ap.add_argument("--tune", action="append", default=[], help="key=value for ngnn_set_tuning, repeatable")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
+for kv in args.tune:
+    k_, v_ = kv.split("=")
+    _lib.call("ngnn_set_tuning", int(k_), int(v_))
 pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
 peak = json.load(open(pk_path))["hbm_gbs"] if os.path.exists(pk_path) else 6650.0
 flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)      # 256 MB, read before each launch (clean eviction)

@@ -16,8 +16,12 @@ from noise_gnn_b200.synthetic import make_dataset  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--tune", action="append", default=[], help="key=value for ngnn_set_tuning, repeatable")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
+for kv in args.tune:
+    k_, v_ = kv.split("=")
+    _lib.call("ngnn_set_tuning", int(k_), int(v_))
 data, sh, train_idx = make_dataset("products", device=dev)
 loader = NeighborLoader(data, input_nodes=train_idx, num_neighbors=list(sh.fanouts), batch_size=sh.batch_size, shuffle=True)
 loader.transpose_hops = 2
@@ -60,10 +64,13 @@ def run(tag):
 
 
 run("warm-up")
-for wide in (0, 1, 2):
-    for threads in (128, 256, 512):
-        _lib.call("ngnn_set_tuning", 9, wide)
-        _lib.call("ngnn_set_tuning", 1, threads)
-        run(f"K-AGG-T variant={wide} threads={threads}")
+for l1 in (0, 1):
+    _lib.call("ngnn_set_tuning", 13, l1)
+    for wide in (0, 1, 2):
+        for threads in (128, 256):
+            _lib.call("ngnn_set_tuning", 9, wide)
+            _lib.call("ngnn_set_tuning", 1, threads)
+            run(f"K-AGG-T variant={wide} threads={threads} l1={l1}")
 _lib.call("ngnn_set_tuning", 9, 0)
 _lib.call("ngnn_set_tuning", 1, 256)
+_lib.call("ngnn_set_tuning", 13, 0)

@@ -1,0 +1,58 @@
+"""K-AGG-T (and the generic K-AGG) on mid-width rows (F = 128, 256) of the Computers-shaped graph: lanes per row, rows in flight,
+L1 allocation and the hub-row threshold.
+    python profiles/prof_mid.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from noise_gnn_b200 import NeighborLoader, _lib, ops  # noqa: E402
+from noise_gnn_b200.synthetic import make_dataset  # noqa: E402
+
+dev = torch.device("cuda", 0)
+flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
+
+
+def timed(fn, reps=9):
+    ms = []
+    for _ in range(reps):
+        flush.sum()
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); z.record(); z.synchronize()
+        ms.append(a.elapsed_time(z))
+    ms.sort()
+    return ms[len(ms) // 2] * 1e3
+
+
+def tune(**kw):
+    for k, v in kw.items():
+        _lib.call("ngnn_set_tuning", int(k[1:]), v)
+
+
+data, sh, _ = make_dataset("computers", device=dev)
+N = data.num_nodes
+for fan in (10, 25):
+    loader = NeighborLoader(data, input_nodes=None, num_neighbors=[fan], batch_size=N, shuffle=False)
+    blk = next(iter(loader)).block
+    n, e = blk.n_rows, blk.e
+    ct, rt = blk.transpose(e, n)
+    for F in (256,):
+        x, out, dm, dx = (torch.randn(n, F, device=dev) for _ in range(4))
+        for wide in (0, 1, 2):
+            for l1 in (0, 1):
+                for lr in (32, 64, 256):
+                    tune(k9=wide, k13=l1, k11=lr)
+                    tb = timed(lambda: ops.agg_bwd(ct, rt, dm, n, out=dx))
+                    print(f"fan={fan:2d} F={F} variant={wide} l1={l1} long_row={lr:4d}  bwd {tb:7.1f} us", flush=True)
+    tune(k9=0, k13=0, k11=64)
+    for F in (128,):
+        x, out, dm, dx = (torch.randn(n, F, device=dev) for _ in range(4))
+        for group in (32, 16, 8):
+            for u in (2, 4, 8):
+                for l1 in (0, 1):
+                    tune(k2=group, k0=u, k13=l1)
+                    tb = timed(lambda: ops.agg_bwd(ct, rt, dm, n, out=dx))
+                    print(f"fan={fan:2d} F={F} group={group:2d} unroll={u} l1={l1}  bwd {tb:7.1f} us", flush=True)
+    tune(k2=32, k0=0, k13=0)

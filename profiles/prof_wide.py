@@ -1,5 +1,5 @@
-"""K-AGG / K-AGG-T on wide rows (F = 767, 1024, 1433) of the Computers-shaped graph, fan-out 10: padded (128-bit kernels) against
-unpadded (scalar kernels) rows and CTA sizes — the part of the C5 sweep that moved between rounds.
+"""K-AGG / K-AGG-T on wide rows (F = 512 .. 1433) of the Computers-shaped graph: the row's warp walking its column chunks
+(ngnn_set_tuning(12, 0)) against the chunks spread over grid.y (1..5 = vectors per lane x neighbour rows in flight).
     python profiles/prof_wide.py"""
 import os
 import sys
@@ -28,28 +28,20 @@ def timed(fn, reps=9):
 
 data, sh, _ = make_dataset("computers", device=dev)
 N = data.num_nodes
-loader = NeighborLoader(data, input_nodes=None, num_neighbors=[10], batch_size=N, shuffle=False)
-blk = next(iter(loader)).block
-n, e = blk.n_rows, blk.e
-ct, rt = blk.transpose(e, n)
-deg = (ct[1:] - ct[:-1])
-print("transposed row lengths: max", int(deg.max()), "p99", int(torch.quantile(deg.float(), 0.99)), "mean", float(deg.float().mean()), flush=True)
-for F in (256, 512, 1024):
-    x = torch.zeros((n, F), device=dev).normal_(); out = torch.zeros((n, F), device=dev); dm = x.clone(); dx = out.clone()
-    for lr in (1024, 128, 64, 48, 32):
-        _lib.call("ngnn_set_tuning", 11, lr)
-        tf = timed(lambda: ops.agg_fwd(blk.rowptr, blk.col, x, n, out=out))
-        tb = timed(lambda: ops.agg_bwd(ct, rt, dm, n, out=dx))
-        print(f"F={F:5d} long_row={lr:5d}  fwd {tf:7.1f} us  bwd {tb:7.1f} us", flush=True)
-_lib.call("ngnn_set_tuning", 11, 64)
-for F in ():
-    for pad in (True, False):
-        ld = (F + 3) // 4 * 4 if pad else F
-        mk = lambda: torch.zeros((n, ld), device=dev)[:, :F] if pad else torch.zeros((n, F), device=dev)
+names = {0: "walk <32,8,1>/<32,4,2>", 2: "split <32,4,2>", 6: "split <32,4,2> L1", 7: "split <32,4,1>", 8: "split <32,4,4>",
+         9: "scalar", 10: "split <32,4,2> T128", 11: "split <32,4,2> T512", 12: "walk <32,4,2> L1", 13: "walk <32,8,1> L1"}
+for fan in (10, 25):
+    loader = NeighborLoader(data, input_nodes=None, num_neighbors=[fan], batch_size=N, shuffle=False)
+    blk = next(iter(loader)).block
+    n, e = blk.n_rows, blk.e
+    ct, rt = blk.transpose(e, n)
+    for F in (512, 767, 1024, 1433):
+        ld = (F + 3) // 4 * 4
+        mk = lambda: torch.zeros((n, ld), device=dev)[:, :F]
         x, out, dm, dx = mk().normal_(), mk(), mk().normal_(), mk()
-        for threads in (128, 256, 512):
-            _lib.call("ngnn_set_tuning", 1, threads)
+        for v in names:
+            _lib.call("ngnn_set_tuning", 12, v)
             tf = timed(lambda: ops.agg_fwd(blk.rowptr, blk.col, x, n, out=out))
             tb = timed(lambda: ops.agg_bwd(ct, rt, dm, n, out=dx))
-            print(f"F={F:5d} {'padded  ' if pad else 'unpadded'} threads={threads:3d}  fwd {tf:7.1f} us  bwd {tb:7.1f} us", flush=True)
-_lib.call("ngnn_set_tuning", 1, 256)
+            print(f"fan={fan:2d} F={F:5d} {names[v]:24s} fwd {tf:7.1f} us  bwd {tb:7.1f} us", flush=True)
+_lib.call("ngnn_set_tuning", 12, 0)
