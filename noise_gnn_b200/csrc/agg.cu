@@ -226,6 +226,176 @@ __global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(Agg
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K-AGG-T with the gate rows staged through shared memory (training backward of a sampled block, 64 < F <= 256):
+//     dX[j] = gate_j * ( sum_{q in CSC row j} dmean[row_t[q]]  +  dX_root[j] )        gate_j = (h_j > 0) * act_scale
+// Nearly every transposed row of a sampled block has ONE entry, and dmean / dX_root (a few thousand rows, just written by
+// K-DGRAD) sit in L2, so the kernel is a stream: read the gate row (the saved layer output h), write the dX row.  In the
+// generic kernel those reads are bounded by registers — 56 rows in flight per SM, ncu: 2.4 TB/s, 57 % of the stall samples
+// waiting for the gate loads.  Here a CTA owns 32 consecutive rows and the copy engine brings their gate rows into shared
+// memory (`cp.async.bulk`, one per row, completing on an mbarrier) while the warps walk extents -> indices -> rows:
+// 6 CTAs x 32 KB per SM in flight at no register cost.  Same summation order as the generic kernel (stored order, then
+// the root row), long rows handed to the whole CTA in the same way => the two kernels are bitwise interchangeable.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {              // bounded: a protocol bug traps instead of hanging the GPU
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+constexpr int kStageTile = 32;      // rows per CTA
+constexpr int kStageThreads = 128;  // 8 half-warps x 4 rows
+template <int VPL>                  // vectors per lane of a 16-lane group: F4 <= 16 * VPL
+__global__ void __launch_bounds__(kStageThreads) k_aggT_staged(AggParams p) {
+  constexpr int G = 16, RPG = kStageTile / (kStageThreads / G), NW = kStageThreads / 32;
+  constexpr int CV = G * VPL / 32;
+  static_assert(CV >= 1, "a full warp covers the group's columns");
+  extern __shared__ __align__(128) unsigned char stage_raw[];       // gate tile: kStageTile rows x F4 vectors
+  __shared__ float4 s_part[NW - 1][CV * 32];                       // warp 0 keeps its own partial sums
+  __shared__ int s_long[kStageTile];
+  __shared__ int s_nlong;
+  __shared__ __align__(8) uint64_t s_bar;
+  pdl_trigger();
+  pdl_wait();
+  float4* s_gate = reinterpret_cast<float4*>(stage_raw);
+  const int F4 = (int)((p.F + 3) >> 2);
+  const int64_t n_rows = agg_rows(p);
+  const int64_t row0 = (int64_t)blockIdx.x * kStageTile;
+  if (row0 >= n_rows) return;                                        // CTA-uniform
+  const int tile_rows = (int)((n_rows - row0) < kStageTile ? (n_rows - row0) : kStageTile);
+  const int tid = threadIdx.x, lane = tid & 31, gl = lane & (G - 1), grp = tid / G, wib = tid >> 5;
+  const unsigned gmask = 0xffffu << ((lane >> 4) * 16);
+  const uint32_t bar = agg_smem_u32(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_nlong = 0;
+  }
+  __syncthreads();
+  if (wib == 0) {
+    if (lane == 0)
+      asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+                   ::"r"(bar), "r"((uint32_t)(tile_rows * F4 * 16)) : "memory");
+    __syncwarp();
+    if (lane < tile_rows)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(agg_smem_u32(s_gate + (size_t)lane * F4)), "l"(p.act_ref + (row0 + lane) * p.ld_act),
+                     "r"((uint32_t)(F4 * 16)), "r"(bar) : "memory");
+  }
+
+  // rows of this group: tile-local r = i * 8 + grp (consecutive groups take consecutive rows).  The three dependent loads of
+  // the four rows are issued as three batches.
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t n_add = p.add != nullptr ? agg_n_add(p) : 0;
+  int beg[RPG], end[RPG], my[RPG];
+#pragma unroll
+  for (int i = 0; i < RPG; ++i) {
+    const int r = i * (kStageThreads / G) + grp;
+    beg[i] = end[i] = 0;
+    if (r < tile_rows) { beg[i] = __ldg(p.ptr + row0 + r); end[i] = __ldg(p.ptr + row0 + r + 1); }
+  }
+#pragma unroll
+  for (int i = 0; i < RPG; ++i) my[i] = (beg[i] + gl < end[i]) ? __ldg(p.idx + beg[i] + gl) : 0;
+
+  bool waited = false;
+#pragma unroll
+  for (int i = 0; i < RPG; ++i) {
+    const int r = i * (kStageThreads / G) + grp;
+    if (r >= tile_rows) continue;
+    const int64_t row = row0 + r;
+    const int deg = end[i] - beg[i];
+    if (deg > p.long_row) {                                          // hub row: the whole CTA reduces it below
+      if (gl == 0) s_long[atomicAdd(&s_nlong, 1)] = r;
+      continue;
+    }
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = zero4;
+    // first window of <= 16 indices is already in registers
+    {
+      const int cnt = min(G, deg);
+      for (int j = 0; j < cnt; j += 2) {
+        float4 v4[2][VPL];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int su = __shfl_sync(gmask, my[i], min(j + u, cnt - 1), G);
+          const float4* src = reinterpret_cast<const float4*>(p.x + (int64_t)su * p.ld_x);
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int c = gl + v * G;
+            v4[u][v] = (c < F4 && j + u < cnt) ? ldg_nc_f4(src + c) : zero4;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) f4_add(acc[v], v4[u][v]);
+      }
+    }
+    if (deg > G) seg_accumulate<G, VPL, 2>(p, beg[i] + G, end[i], 0, F4, gl, gmask, acc);
+    if (!waited) { agg_mbar_wait(bar, 0); waited = true; }
+    const bool has_add = row < n_add;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = gl + v * G;
+      if (c >= F4) continue;
+      float4 o = acc[v];
+      if (has_add) f4_add(o, ldg_nc_f4(reinterpret_cast<const float4*>(p.add + row * p.ld_add) + c));
+      const float4 h = s_gate[(size_t)r * F4 + c];
+      o.x = h.x > 0.f ? o.x * p.act_scale : 0.f;
+      o.y = h.y > 0.f ? o.y * p.act_scale : 0.f;
+      o.z = h.z > 0.f ? o.z * p.act_scale : 0.f;
+      o.w = h.w > 0.f ? o.w * p.act_scale : 0.f;
+      reinterpret_cast<float4*>(p.out + row * p.ld_out)[c] = o;
+    }
+  }
+  __syncthreads();
+  const int nlong = s_nlong;                                         // CTA-uniform
+  if (nlong == 0) return;
+  if (!waited) agg_mbar_wait(bar, 0);
+  for (int k = 0; k < nlong; ++k) {
+    const int r = s_long[k];
+    const int64_t lrow = row0 + r;
+    const int lbeg = __ldg(p.ptr + lrow), lend = __ldg(p.ptr + lrow + 1);
+    const int slice = ((lend - lbeg + NW - 1) / NW + 31) & ~31;      // whole 32-index windows per warp
+    const int sb = min(lend, lbeg + wib * slice), se = min(lend, sb + slice);
+    const bool has_add = lrow < n_add;
+    for (int c0 = 0; c0 < F4; c0 += 32 * CV) {
+      float4 acc[CV];
+#pragma unroll
+      for (int v = 0; v < CV; ++v) acc[v] = zero4;
+      seg_accumulate<32, CV, 2>(p, sb, se, c0, F4, lane, 0xffffffffu, acc);
+      if (wib > 0) {
+#pragma unroll
+        for (int v = 0; v < CV; ++v) s_part[wib - 1][v * 32 + lane] = acc[v];
+      }
+      __syncthreads();
+      if (wib == 0) {
+#pragma unroll
+        for (int v = 0; v < CV; ++v) {
+          for (int w = 1; w < NW; ++w) f4_add(acc[v], s_part[w - 1][v * 32 + lane]);  // fixed warp order
+          const int c = c0 + lane + v * 32;
+          if (c >= F4) continue;
+          float4 o = acc[v];
+          if (has_add) f4_add(o, ldg_nc_f4(reinterpret_cast<const float4*>(p.add + lrow * p.ld_add) + c));
+          const float4 h = s_gate[(size_t)r * F4 + c];
+          o.x = h.x > 0.f ? o.x * p.act_scale : 0.f;
+          o.y = h.y > 0.f ? o.y * p.act_scale : 0.f;
+          o.z = h.z > 0.f ? o.z * p.act_scale : 0.f;
+          o.w = h.w > 0.f ? o.w * p.act_scale : 0.f;
+          reinterpret_cast<float4*>(p.out + lrow * p.ld_out)[c] = o;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // Scalar variant for rows that are not 16-byte addressable (F % 4 != 0, e.g. 1433 or 767).
 template <int VPL>
 __global__ void __launch_bounds__(256) k_seg_reduce_scalar(AggParams p) {
@@ -396,6 +566,7 @@ static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 
 static int g_tune_keep = 1;      // ngnn_set_tuning(7, 0|1): L2 evict_last priority on the layer-1 table gathers
 static int g_tune_long = kLongRow;  // ngnn_set_tuning(11, n): hub-row threshold of the generic kernel
 static int g_tune_xwide = 0;     // ngnn_set_tuning(12, v): F > 256: 0 = column chunks on grid.y (default); 1 = the row's warp walks them; 2 = 128-thread CTAs
+static int g_tune_stage = 1;     // ngnn_set_tuning(14, 0|1): K-AGG-T of the training backward through the shared-memory staged kernel
 static int g_tune_l1 = 0;        // ngnn_set_tuning(13, v): gathers of the generic kernel allocate in L1: 0 = wide rows only, 1 = always, 2 = never
 static int g_tune_wide = 0;      // ngnn_set_tuning(9, v): generic kernel for 128 < F <= 256: 0 = half-warp/row x4 vectors, 128-thread
                                  //   CTAs (default); 1 = warp/row x2 vectors unroll 2; 2 = warp/row unroll 4
@@ -428,7 +599,10 @@ static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
   if (p.bias) vec = vec && is_aligned(p.bias, 16) && p.F % 4 == 0;
   if (vec) {
     const bool fwd_plain = p.add == nullptr && p.act_ref == nullptr && p.bias == nullptr;   // forward aggregation (mean [+ root gather])
-    if (fwd_plain && g_tune_pipe && F4 > 16 && F4 <= 64) {
+    // The persistent pipelined kernel deals rows to warps statically: right for the near-uniform row lengths of a sampled
+    // block's forward (<= fan-out), wrong for a transposed block / an un-sampled graph (sum form), whose hub rows would each be
+    // walked by one warp — Computers-shaped transpose, F = 256, fan-out 25: 90 us there, 61 us in the generic kernel.
+    if (fwd_plain && p.mean && g_tune_pipe && F4 > 16 && F4 <= 64) {
       if (F4 <= 32) {
         const int u = g_tune_unroll;
         if (p.root_idx) {
@@ -446,6 +620,15 @@ static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
       NGNN_LAUNCH_CHECK();
       return NGNN_OK;
     }
+    // training backward of a sampled block (gate present, sum form): gate rows staged through shared memory
+    if (g_tune_stage && !p.mean && p.act_ref != nullptr && p.bias == nullptr && p.root_idx == nullptr && F4 > 16 && F4 <= 64) {
+      const unsigned grid = (unsigned)ceil_div(p.n_rows, (int64_t)kStageTile);
+      const size_t smem = (size_t)kStageTile * F4 * 16;
+      if (F4 <= 32) launch_chain(k_aggT_staged<2>, dim3(grid), dim3(kStageThreads), smem, st, p);
+      else launch_chain(k_aggT_staged<4>, dim3(grid), dim3(kStageThreads), smem, st, p);
+      NGNN_LAUNCH_CHECK();
+      return NGNN_OK;
+    }
     if (F4 <= 8) launch_v4<8, 1, 8>(p, st);
     else if (F4 <= 16) launch_v4<16, 1, 8>(p, st);
     else if (F4 <= 32) {
@@ -457,7 +640,10 @@ static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
     else if (F4 <= 64) {
       // measured on the layer-2 backward of a products block (77 k rows x 256, mostly one transposed neighbour per row;
       // profiles/prof_aggT.py): warp per row 61 us, half-warp per row with 128-thread CTAs 47 us (twice the rows in flight)
-      if (g_tune_wide == 2) launch_v4<32, 2, 4>(p, st);
+      // ... and (profiles/prof_mid.py) on transposed rows of mean length 10-25 without a gate: warp per row, 4 rows in flight 61 us,
+      // against 82 us for the half-warp form
+      const bool short_rows = p.act_ref != nullptr || p.add != nullptr;      // training backward of a sampled block
+      if (g_tune_wide == 2 || (g_tune_wide == 0 && !short_rows)) launch_v4<32, 2, 4>(p, st);
       else if (g_tune_wide == 1) launch_v4<32, 2, 2>(p, st);
       else launch_v4<16, 4, 2>(p, st, 128);
     }
@@ -545,6 +731,7 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 10 && (value == 0 || value == 1)) { g_use_pdl = value; return NGNN_OK; }
   if (key == 12 && value >= 0 && value <= 2) { g_tune_xwide = value; return NGNN_OK; }
   if (key == 13 && value >= 0 && value <= 2) { g_tune_l1 = value; return NGNN_OK; }
+  if (key == 14 && (value == 0 || value == 1)) { g_tune_stage = value; return NGNN_OK; }
   if (key == 11 && value >= 32 && value <= (1 << 20)) { g_tune_long = value; return NGNN_OK; }
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }

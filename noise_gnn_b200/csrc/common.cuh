@@ -45,7 +45,13 @@ static inline cudaStream_t as_stream(ngnn_stream_t s) { return reinterpret_cast<
 // pdl_wait() until the predecessor has completed and flushed — its CTAs are already resident when that happens.
 // Both instructions are no-ops for a kernel launched the ordinary way.  The attribute is OFF by default (measured slower on the
 // full step, see abi.cu); ngnn_set_tuning(10, 1) turns it on.
+#ifdef NGNN_PDL_EARLY
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+// Without the early trigger a dependent launch is released when every CTA of its predecessor has exited (the implicit
+// trigger): no early residency, only the completion / launch hand-off is shortened.
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 extern int g_use_pdl;
 template <typename... KArgs, typename... Args>

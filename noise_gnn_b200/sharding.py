@@ -44,6 +44,12 @@ class SeedSharder:
         """Global batch trained by this rank at local step `step` (wraps around in the last, padded round)."""
         return (step * self.world_size + self.rank) % max(self.num_batches_global, 1)
 
+    @property
+    def full_len(self) -> int:
+        """Seeds of a full batch: ``batch_size``, or every seed when there are fewer (the reference's full-batch configs:
+        pubmed's 60 train seeds, cora's 140, with batch_size 512)."""
+        return min(self.batch_size, len(self.input_nodes))
+
     def batch_len(self, global_batch_idx: int) -> int:
         """Number of seeds of a global batch (only the epoch's last batch can be short)."""
         n = len(self.input_nodes)
@@ -71,7 +77,7 @@ class SeedSharder:
         for such rounds, so that all ranks take the same decision: a collective captured in a CUDA graph on one rank must not
         meet an eagerly issued one on another."""
         last = step * self.world_size + self.world_size - 1
-        return last < self.num_batches_global and self.batch_len(last) == self.batch_size
+        return last < self.num_batches_global and self.batch_len(last) == self.full_len
 
     def batch_seeds(self, order: torch.Tensor, global_batch_idx: int) -> torch.Tensor:
         b = global_batch_idx % max(self.num_batches_global, 1)

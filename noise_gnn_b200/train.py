@@ -291,7 +291,7 @@ class Trainer:
             sh = loader.sharder
             spe = len(loader)                                   # steps per epoch on this rank
             L = self._cfg["num_layers"]
-            bs_full = loader.batch_size
+            bs_full = sh.full_len
             steps0 = self.steps                                 # the step that consumes schedule entry j is number steps0 + j + 1
             cur = torch.cuda.current_stream()
             side = loader.__dict__.get("_side")

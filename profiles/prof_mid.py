@@ -38,21 +38,12 @@ for fan in (10, 25):
     blk = next(iter(loader)).block
     n, e = blk.n_rows, blk.e
     ct, rt = blk.transpose(e, n)
-    for F in (256,):
+    for F in (64, 128, 256):
         x, out, dm, dx = (torch.randn(n, F, device=dev) for _ in range(4))
-        for wide in (0, 1, 2):
-            for l1 in (0, 1):
-                for lr in (32, 64, 256):
-                    tune(k9=wide, k13=l1, k11=lr)
-                    tb = timed(lambda: ops.agg_bwd(ct, rt, dm, n, out=dx))
-                    print(f"fan={fan:2d} F={F} variant={wide} l1={l1} long_row={lr:4d}  bwd {tb:7.1f} us", flush=True)
-    tune(k9=0, k13=0, k11=64)
-    for F in (128,):
-        x, out, dm, dx = (torch.randn(n, F, device=dev) for _ in range(4))
-        for group in (32, 16, 8):
-            for u in (2, 4, 8):
-                for l1 in (0, 1):
-                    tune(k2=group, k0=u, k13=l1)
-                    tb = timed(lambda: ops.agg_bwd(ct, rt, dm, n, out=dx))
-                    print(f"fan={fan:2d} F={F} group={group:2d} unroll={u} l1={l1}  bwd {tb:7.1f} us", flush=True)
-    tune(k2=32, k0=0, k13=0)
+        for pipe in (1, 0):
+            for wide in ((0, 1, 2) if (F == 256 and pipe == 0) else (0,)):
+                tune(k3=pipe, k9=wide)
+                tf = timed(lambda: ops.agg_fwd(blk.rowptr, blk.col, x, n, out=out))
+                tb = timed(lambda: ops.agg_bwd(ct, rt, dm, n, out=dx))
+                print(f"fan={fan:2d} F={F} pipe={pipe} variant={wide}  fwd {tf:7.1f} us  bwd {tb:7.1f} us", flush=True)
+tune(k3=1, k9=0)

@@ -34,6 +34,12 @@ def test_sharder_deals_global_batches_round_robin():
     assert len(SeedSharder(nodes, 10, True, drop_last=True)) == 10
     with pytest.raises(ValueError):
         SeedSharder(nodes, 10, True, rank=2, world_size=2)
+    # full-batch configs (fewer seeds than batch_size): the one batch is "full", a genuinely short last batch is not
+    fb = SeedSharder(torch.arange(60), 512, True)
+    assert len(fb) == 1 and fb.full_len == 60 and fb.round_is_full(0)
+    assert single.full_len == 10 and single.round_is_full(9) and not single.round_is_full(10)
+    two = [SeedSharder(nodes, 10, True, 1232, rank=r, world_size=2) for r in range(2)]
+    assert all(s.round_is_full(4) for s in two) and not any(s.round_is_full(5) for s in two)    # round 5 = batch 10 (3 seeds) + filler
 
 
 def _free_port():

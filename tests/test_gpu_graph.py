@@ -191,3 +191,29 @@ def test_train_epoch_max_steps_and_resident_seeds(dev):
     la, ca, _ = a.train_epoch(loader, epoch=0, max_steps=7)
     lb, cb, _ = b.train_epoch(loader, epoch=0, max_steps=7, seeds_resident=True, log_every_step=False)
     assert la == lb and ca == cb and torch.equal(a.buckets.param, b.buckets.param)
+
+
+def test_full_batch_config_replays_across_epochs(dev):
+    """The reference's full-batch configs (pubmed: 60 train seeds, cora: 140, batch_size 512): one batch per epoch, shorter than
+    batch_size.  Every round is 'full' (all the seeds), so run_steps replays the captured step across epoch boundaries; the
+    losses equal the eager batch-by-batch loop's."""
+    from noise_gnn_b200.train import Trainer
+    fan, L, epochs = [10, 5], 3, 8
+    data, sh, loader, ref, net = _problem(dev, fan, 512, 0.0, L=L, name="pubmed", scale=1.0)
+    _, _, loader2, _, net2 = _problem(dev, fan, 512, 0.0, L=L, name="pubmed", scale=1.0)
+    assert len(loader) == 1 and loader.sharder.full_len == 60
+    net.train(); net2.train()
+    tr = Trainer(net, lr=1e-3)
+    total, correct, log = tr.run_steps(loader, epochs, start_epoch=0)
+    assert tr.graph_replays == epochs - 3                      # two eager steps, then replays; the last step has no next block
+    losses = np.diff(np.concatenate([[0.0], log[:, 0].numpy()]))
+    tr2 = Trainer(net2, lr=1e-3, use_graph=False)
+    eager = []
+    for ep in range(epochs):
+        loader2.epoch = ep
+        for batch in loader2:
+            assert batch.batch_size == 60
+            tr2.reset_stats()
+            tr2.train_step(batch)
+            eager.append(tr2.read_stats()[0])
+    assert np.allclose(losses, eager, rtol=2e-5, atol=1e-6), (losses, eager)

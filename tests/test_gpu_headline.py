@@ -282,3 +282,45 @@ def test_full_scale_products_step_matches_oracle(dev, products_full, dropout):
                 h = h * masks[i][: h.size(0)].to(h.dtype) / (1.0 - dropout)
     n_gates = sum(int(m.numel()) for m in relu_masks)
     assert flips <= max(64, n_gates // 100_000), (flips, n_gates)   # a handful of 2e7 gates sit within rounding of zero
+
+
+@pytest.mark.parametrize("F,n_src,n_dst", [(256, 77000, 7600), (100, 50000, 9000), (200, 33, 7), (132, 4100, 4100)])
+def test_agg_bwd_staged_gate_kernel(dev, F, n_src, n_dst):
+    """K-AGG-T of the training backward (gate + root rows; the gate rows staged through shared memory by bulk copies) at
+    the products layer-2 shape: mostly one transposed entry per row, some empty rows, a few hub rows handed to the whole CTA,
+    a ragged last tile; against the fp64 formula and bit for bit against the generic kernel."""
+    from noise_gnn_b200 import _lib, ops
+    g = torch.Generator().manual_seed(F + n_src)
+    deg = torch.randint(0, 3, (n_src,), generator=g)
+    deg[torch.randint(0, n_src, (max(n_src // 2000, 2),), generator=g)] = 300          # hubs (> the 64-entry threshold)
+    deg[5] = 17                                                                       # a second index window, not a hub
+    colptr = torch.cat([torch.zeros(1, dtype=torch.long), deg.cumsum(0)])
+    e = int(colptr[-1])
+    row_t = torch.randint(0, n_dst, (e,), generator=g)
+    ld = (F + 3) // 4 * 4
+    pad = lambda t: _pad4(t) if ld != F else t
+    dmean, droot = torch.randn(n_dst, F, generator=g), torch.randn(n_dst, F, generator=g)
+    h = torch.randn(n_src, F, generator=g)
+    h[h.abs() < 0.3] = 0.0                                                            # exact zeros gate to zero
+    want = torch.zeros(n_src, F, dtype=torch.float64)
+    want.index_add_(0, torch.repeat_interleave(torch.arange(n_src), deg), dmean.double()[row_t])
+    want[:n_dst] += droot.double()
+    want = torch.where(h > 0, want * 2.0, torch.zeros_like(want))
+    d = dict(ct=colptr.int().to(dev), rt=row_t.int().to(dev), dm=pad(dmean.to(dev)), dr=pad(droot.to(dev)), h=pad(h.to(dev)))
+    outs = []
+    for staged in (1, 0):
+        _lib.call("ngnn_set_tuning", 14, staged)
+        out = pad(torch.full((n_src, F), float("nan"), device=dev))
+        ops.agg_bwd(d["ct"], d["rt"], d["dm"], n_src, dx_root=d["dr"], n_root=n_dst, act_ref=d["h"], act_scale=2.0, out=out)
+        outs.append(out.clone())
+    _lib.call("ngnn_set_tuning", 14, 1)
+    assert rel_err(outs[0], want) < RTOL
+    if F > 128:
+        assert torch.equal(outs[0], outs[1])                  # same summation order as the generic kernel's half-warp form
+    else:
+        assert rel_err(outs[0], outs[1]) < 1e-6               # (narrower rows: the generic kernel cuts hub rows into 8 slices, not 4)
+    # without root rows
+    out = ops.agg_bwd(d["ct"], d["rt"], d["dm"], n_src, act_ref=d["h"], act_scale=1.0)
+    want2 = torch.zeros(n_src, F, dtype=torch.float64)
+    want2.index_add_(0, torch.repeat_interleave(torch.arange(n_src), deg), dmean.double()[row_t])
+    assert rel_err(out, torch.where(h > 0, want2, torch.zeros_like(want2))) < RTOL
