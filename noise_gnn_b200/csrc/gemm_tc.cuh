@@ -311,6 +311,7 @@ struct TcGemmParams {
   int32_t BN;                 // UMMA N / columns per CTA tile
   int32_t kblocks1, kblocks2; // K-blocks of operand pair 1 / 2 covered by THIS launch
   int32_t kb_begin1, kb_begin2; // first K-block of each pair this launch covers (a long contraction is cut into several launches)
+  int32_t ktail1, ktail2;     // 8-float k-steps that hold data in the LAST K-block of pair 1 / 2 of this launch (1..4): the rest is TMA zero fill
   int32_t acc_in, final;      // acc_in: add the output the previous launch left; final: apply bias / scale / activation / dropout
   int32_t b_koff2;            // k offset (floats) of pair 2 in the packed B planes
   int32_t stages;
@@ -461,8 +462,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUte
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + a_span, b_lo = b_hi + b_bytes;
         const uint32_t ta = tmem_base + tmem_a0 + (uint32_t)s * TS_A_COLS;
+        // a ragged K (products layer 1: K = 200 = 6 K-blocks + 8 floats) leaves all-zero k-steps in the last K-block: not issued
+        const int nk = (kb == p.kblocks1 - 1) ? p.ktail1 : (kb == KB - 1 ? p.ktail2 : TC_BK / 8);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
+          if (k >= nk) break;
           const uint32_t koff = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle atom
           const uint64_t dbh = umma_desc_k_sw128(b_hi + koff), dbl = umma_desc_k_sw128(b_lo + koff);
           if (TS) {
@@ -815,6 +819,8 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
   }
   // one launch per accumulation chain of at most TC_CHAIN_KBLOCKS K-blocks (a single launch for every F <= 512)
   const int32_t kb1 = p.kblocks1, kb2 = p.kblocks2, total = kb1 + kb2;
+  const int64_t k_op = concat_k ? 2 * F : F;                         // floats of data along K per operand
+  const int32_t tail = (int32_t)((k_op - 1) % TC_BK) / 8 + 1, tail1 = tail, tail2 = tail;
   const int32_t chains = (total + TC_MAX_CHAIN_KBLOCKS - 1) / TC_MAX_CHAIN_KBLOCKS <= 1 ? 1 : (total + TC_CHAIN_KBLOCKS - 1) / TC_CHAIN_KBLOCKS;
   const int32_t per = (total + chains - 1) / chains;
   for (int32_t c = 0; c < chains; ++c) {
@@ -823,6 +829,7 @@ static inline int32_t tc_gemm_fwd(const float* a_l, int64_t ld_al, const float* 
     const int32_t b0 = g0 > kb1 ? g0 - kb1 : 0, b1 = g1 > kb1 ? g1 - kb1 : 0;   // part in operand 2
     TcGemmParams pc = p;
     pc.kblocks1 = o1e - o1b; pc.kb_begin1 = o1b; pc.kblocks2 = b1 - b0; pc.kb_begin2 = b0;
+    pc.ktail1 = (o1e == kb1) ? tail1 : 4; pc.ktail2 = (b1 == kb2) ? tail2 : 4;
     pc.acc_in = c > 0; pc.final = c == chains - 1;
     const int32_t rc = tc_launch(tA1, tA2, *mBh, *mBl, pc, pl, 1, st);
     if (rc != NGNN_OK) return rc;
@@ -879,6 +886,7 @@ static inline int32_t tc_gemm_dgrad(const float* dy, int64_t ld_dy, const float*
   TcGemmParams p{};
   p.M = (int32_t)n; p.M_dev = n_dev; p.BN = pl.BN; p.stages = pl.stages; p.tiles_per_seg = pl.tiles_per_seg;
   p.kblocks1 = Kpack / TC_BK; p.kblocks2 = 0; p.b_koff2 = 0; p.final = 1;
+  p.ktail1 = (int32_t)((O - 1) % TC_BK) / 8 + 1; p.ktail2 = 4;
   p.rowptr = rowptr;
   int ns = 0;
   if (dmean) p.seg[ns++] = TcSegment{dmean, ld_dmean, (int32_t)F, 0, rowptr != nullptr ? 1 : 0};

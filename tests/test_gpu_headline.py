@@ -308,7 +308,7 @@ def test_agg_bwd_staged_gate_kernel(dev, F, n_src, n_dst):
     want = torch.where(h > 0, want * 2.0, torch.zeros_like(want))
     d = dict(ct=colptr.int().to(dev), rt=row_t.int().to(dev), dm=pad(dmean.to(dev)), dr=pad(droot.to(dev)), h=pad(h.to(dev)))
     outs = []
-    for staged in (1, 0):
+    for staged in (2, 0):                                     # 2 = the staged kernel whatever the row count
         _lib.call("ngnn_set_tuning", 14, staged)
         out = pad(torch.full((n_src, F), float("nan"), device=dev))
         ops.agg_bwd(d["ct"], d["rt"], d["dm"], n_src, dx_root=d["dr"], n_root=n_dst, act_ref=d["h"], act_scale=2.0, out=out)
@@ -320,7 +320,9 @@ def test_agg_bwd_staged_gate_kernel(dev, F, n_src, n_dst):
     else:
         assert rel_err(outs[0], outs[1]) < 1e-6               # (narrower rows: the generic kernel cuts hub rows into 8 slices, not 4)
     # without root rows
+    _lib.call("ngnn_set_tuning", 14, 2)
     out = ops.agg_bwd(d["ct"], d["rt"], d["dm"], n_src, act_ref=d["h"], act_scale=1.0)
+    _lib.call("ngnn_set_tuning", 14, 1)
     want2 = torch.zeros(n_src, F, dtype=torch.float64)
     want2.index_add_(0, torch.repeat_interleave(torch.arange(n_src), deg), dmean.double()[row_t])
     assert rel_err(out, torch.where(h > 0, want2, torch.zeros_like(want2))) < RTOL
