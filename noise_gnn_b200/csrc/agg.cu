@@ -232,9 +232,11 @@ __global__ void __launch_bounds__(seg_max_threads<G, VPL>()) k_seg_reduce_v4(Agg
 // Nearly every transposed row of a sampled block has ONE entry, and dmean / dX_root (a few thousand rows, just written by
 // K-DGRAD) sit in L2, so the kernel is a stream: read the gate row (the saved layer output h), write the dX row.  In the
 // generic kernel those reads are bounded by registers — 56 rows in flight per SM, ncu: 2.4 TB/s, 57 % of the stall samples
-// waiting for the gate loads.  Here a CTA owns 32 consecutive rows and the copy engine brings their gate rows into shared
-// memory (`cp.async.bulk`, one per row, completing on an mbarrier) while the warps walk extents -> indices -> rows:
-// 6 CTAs x 32 KB per SM in flight at no register cost.  Same summation order as the generic kernel (stored order, then
+// waiting for the gate loads.  Here a CTA owns 8 x RPG consecutive rows and the copy engine brings their gate rows into shared
+// memory (`cp.async.bulk`, one per row, completing on an mbarrier) while the half-warps walk extents -> indices -> rows,
+// RPG rows each: the gate bytes in flight cost no registers.  RPG = 2 measured best (products step 0.410 ms with the
+// generic kernel, 0.394 with RPG = 4, 0.391 with RPG = 2; the arxiv-shaped block, whose transposed rows are longer, 0.233 /
+// 0.243 / 0.229: with 4 rows per half-warp too few gather chains are in flight).  Same summation order as the generic kernel (stored order, then
 // the root row), long rows handed to the whole CTA in the same way => the two kernels are bitwise interchangeable.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -248,11 +250,10 @@ __device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
-constexpr int kStageTile = 32;      // rows per CTA
-constexpr int kStageThreads = 128;  // 8 half-warps x 4 rows
-template <int VPL>                  // vectors per lane of a 16-lane group: F4 <= 16 * VPL
-__global__ void __launch_bounds__(kStageThreads) k_aggT_staged(AggParams p) {
-  constexpr int G = 16, RPG = kStageTile / (kStageThreads / G), NW = kStageThreads / 32;
+constexpr int kStageThreads = 128;  // 8 half-warps x RPG rows
+template <int VPL, int RPG>         // vectors per lane of a 16-lane group: F4 <= 16 * VPL; rows per group
+__global__ void __launch_bounds__(kStageThreads, RPG == 4 ? 6 : (RPG == 2 ? 7 : 8)) k_aggT_staged(AggParams p) {
+  constexpr int G = 16, kStageTile = RPG * (kStageThreads / G), NW = kStageThreads / 32;
   constexpr int CV = G * VPL / 32;
   static_assert(CV >= 1, "a full warp covers the group's columns");
   extern __shared__ __align__(128) unsigned char stage_raw[];       // gate tile: kStageTile rows x F4 vectors
@@ -543,6 +544,7 @@ __global__ void __launch_bounds__(256) k_agg_fwd_pipe(AggParams p) {
   }
 }
 
+static int g_tune_small = 1;     // ngnn_set_tuning(15, 0|1): few-row form of the pipelined K-AGG (64-thread CTAs, 8 rows in flight)
 template <int VPL, int U, bool ROOT>
 static void launch_pipe(const AggParams& p, cudaStream_t st) {
   static int blocks_per_sm = 0;
@@ -555,7 +557,7 @@ static void launch_pipe(const AggParams& p, cudaStream_t st) {
   }
   int64_t grid = (int64_t)kNumSMs * blocks_per_sm;                 // persistent: one resident wave
   const int64_t need = ceil_div(p.n_rows, 8);                        // 8 warps per CTA
-  if (need < kNumSMs) {
+  if (need < kNumSMs && g_tune_small) {
     // fewer rows than one 256-thread CTA per SM (the top layers of a step): 64-thread CTAs spread the rows over every SM
     launch_chain(k_agg_fwd_pipe<VPL, U, ROOT>, dim3((unsigned)ceil_div(p.n_rows, 2)), dim3(64), 0, st, p);
     return;
@@ -571,7 +573,7 @@ static int g_tune_group = 32;    // ngnn_set_tuning(2, g): lanes per row for 64 
 static int g_tune_keep = 1;      // ngnn_set_tuning(7, 0|1): L2 evict_last priority on the layer-1 table gathers
 static int g_tune_long = kLongRow;  // ngnn_set_tuning(11, n): hub-row threshold of the generic kernel
 static int g_tune_xwide = 0;     // ngnn_set_tuning(12, v): F > 256: 0 = column chunks on grid.y (default); 1 = the row's warp walks them; 2 = 128-thread CTAs
-static int g_tune_stage = 1;     // ngnn_set_tuning(14, 0|1): K-AGG-T of the training backward through the shared-memory staged kernel
+static int g_tune_stage = 1;     // ngnn_set_tuning(14, v): staged K-AGG-T: 0 off, 1 = 2 rows per half-warp (default), 2 = also for few rows (tests), 3 = 4 rows, 4 = 1 row
 static int g_tune_l1 = 0;        // ngnn_set_tuning(13, v): gathers of the generic kernel allocate in L1: 0 = wide rows only, 1 = always, 2 = never
 static int g_tune_wide = 0;      // ngnn_set_tuning(9, v): generic kernel for 128 < F <= 256: 0 = half-warp/row x4 vectors, 128-thread
                                  //   CTAs (default); 1 = warp/row x2 vectors unroll 2; 2 = warp/row unroll 4
@@ -622,7 +624,7 @@ static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
       } else {
         // few rows (the last layer: one row per seed): occupancy is no concern, 8 neighbour rows in flight per lane
         if (p.root_idx) launch_pipe<2, 4, true>(p, st);
-        else if (p.n_rows <= 2048) launch_pipe<2, 8, false>(p, st);
+        else if (p.n_rows <= 2048 && g_tune_small) launch_pipe<2, 8, false>(p, st);
         else launch_pipe<2, 4, false>(p, st);
       }
       NGNN_LAUNCH_CHECK();
@@ -631,11 +633,19 @@ static int32_t run_agg(const AggParams& p_in, cudaStream_t st) {
     // training backward of a sampled block (gate present, sum form): gate rows staged through shared memory
     // (from ~4 tiles per SM up: the 7.6 k-row transpose of the layer above measured 9.6 us in the generic kernel, 14 us here)
     if (g_tune_stage && !p.mean && p.act_ref != nullptr && p.bias == nullptr && p.root_idx == nullptr && F4 > 16 && F4 <= 64 &&
-        (p.n_rows >= (int64_t)kNumSMs * 4 * kStageTile || g_tune_stage == 2)) {
-      const unsigned grid = (unsigned)ceil_div(p.n_rows, (int64_t)kStageTile);
-      const size_t smem = (size_t)kStageTile * F4 * 16;
-      if (F4 <= 32) launch_chain(k_aggT_staged<2>, dim3(grid), dim3(kStageThreads), smem, st, p);
-      else launch_chain(k_aggT_staged<4>, dim3(grid), dim3(kStageThreads), smem, st, p);
+        (p.n_rows >= (int64_t)kNumSMs * 4 * 32 || g_tune_stage == 2)) {
+      const int rpg = g_tune_stage == 3 ? 4 : (g_tune_stage == 4 ? 1 : 2), tile = rpg * (kStageThreads / 16);
+      const unsigned grid = (unsigned)ceil_div(p.n_rows, (int64_t)tile);
+      const size_t smem = (size_t)tile * F4 * 16;
+      if (F4 <= 32) {
+        if (rpg == 2) launch_chain(k_aggT_staged<2, 2>, dim3(grid), dim3(kStageThreads), smem, st, p);
+        else if (rpg == 1) launch_chain(k_aggT_staged<2, 1>, dim3(grid), dim3(kStageThreads), smem, st, p);
+        else launch_chain(k_aggT_staged<2, 4>, dim3(grid), dim3(kStageThreads), smem, st, p);
+      } else {
+        if (rpg == 2) launch_chain(k_aggT_staged<4, 2>, dim3(grid), dim3(kStageThreads), smem, st, p);
+        else if (rpg == 1) launch_chain(k_aggT_staged<4, 1>, dim3(grid), dim3(kStageThreads), smem, st, p);
+        else launch_chain(k_aggT_staged<4, 4>, dim3(grid), dim3(kStageThreads), smem, st, p);
+      }
       NGNN_LAUNCH_CHECK();
       return NGNN_OK;
     }
@@ -741,7 +751,8 @@ int32_t ngnn_set_tuning(int32_t key, int32_t value) {
   if (key == 10 && (value == 0 || value == 1)) { g_use_pdl = value; return NGNN_OK; }
   if (key == 12 && value >= 0 && value <= 2) { g_tune_xwide = value; return NGNN_OK; }
   if (key == 13 && value >= 0 && value <= 2) { g_tune_l1 = value; return NGNN_OK; }
-  if (key == 14 && value >= 0 && value <= 2) { g_tune_stage = value; return NGNN_OK; }   // 2 = also for few rows (tests)
+  if (key == 15 && (value == 0 || value == 1)) { g_tune_small = value; return NGNN_OK; }
+  if (key == 14 && value >= 0 && value <= 4) { g_tune_stage = value; return NGNN_OK; }   // 2 = also for few rows (tests)
   if (key == 11 && value >= 32 && value <= (1 << 20)) { g_tune_long = value; return NGNN_OK; }
   if (key == 6 && (value == 0 || value == 1)) return ngnn_set_gemm_ts(value);
   if (key == 7 && (value == 0 || value == 1)) { g_tune_keep = value; return NGNN_OK; }
