@@ -172,6 +172,7 @@ class BlockSlot:
         self.nt = torch.empty(loader.max_nodes, **i32) if loader.remap is not None else None
         self.seeds = torch.zeros(loader.batch_size, dtype=torch.int64, device=dev)
         self.ctl = torch.zeros(8, **i32)                       # ngnn_step_ctl_t
+        self.ctl_next = torch.zeros(8, **i32)                  # the control words of the NEXT block of this slot, staged ahead
         self.trans = []
         self.ensure_transposes(loader, transposes)
         self.owner = None                                      # weakref to the Batch handed out on these buffers

@@ -207,7 +207,7 @@ class Trainer:
             gs = dict(key=key, loader=loader, tgt=tgt, lab=lab, ms=ms, arena=arena, table=table, H=H, T=T,
                       capture_stream=torch.cuda.Stream(device=arena.device),
                       slots=loader.fixed_slots(2, T), side=torch.cuda.Stream(device=arena.device), graphs=[None, None],
-                      graph_launches=[0, 0])
+                      graph_launches=[0, 0], stage=torch.cuda.Stream(device=arena.device), staged=[None, None], freed=[None, None])
             self._gs = gs
         return gs
 
@@ -258,7 +258,9 @@ class Trainer:
         if bs_next > 0:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                loader.launch_sample(gs["slots"][1 - k], None, bs_next, 0, 0, use_ctl=True, transposes=gs["T"])
+                nxt = gs["slots"][1 - k]
+                nxt.ctl.copy_(nxt.ctl_next, non_blocking=True)      # the staged control words become the slot's live ones
+                loader.launch_sample(nxt, None, bs_next, 0, 0, use_ctl=True, transposes=gs["T"])
         bd = self._slot_desc(gs, k, bs_cur)
         bd.weights_prepared = 1
         _lib.call("ngnn_sage_step", ctypes.byref(ms), ops._ptr(self.buckets.param), ops._ptr(self.buckets.grad), ctypes.byref(bd),
@@ -305,26 +307,48 @@ class Trainer:
                     orders[epoch] = o.to(dev) if seeds_resident else o.pin_memory()
                 return orders[epoch]
 
+            stage = gs["stage"]
+            stage.wait_stream(cur)                              # whatever used the slots before this call has been enqueued on `cur`
+            gs["staged"], gs["freed"] = [None, None], [None, None]
+
             def stage_block(j, k):
-                """seed ids + control words of schedule entry j into slot k (stream-ordered; nothing the host must keep alive)"""
+                """Seed ids + control words of schedule entry j into slot k's staging fields, on the staging stream: they are
+                only read by the sampler of the pair that runs one step later, so the copies run under the current step
+                instead of between two graph launches.  Returns the batch length."""
                 epoch, i = start_epoch + (start_step + j) // spe, (start_step + j) % spe
                 g = sh.global_batch_index(i)
                 bs, w = sh.batch_len(g), sh.loss_scale(i)
                 slot = gs["slots"][k]
-                slot.seeds[:bs].copy_(loader.batch_seeds(order_of(epoch), g), non_blocking=True)
-                _lib.call("ngnn_step_ctl_set", ops._ptr(slot.ctl), epoch & 0xFFFFFFFF, g & 0xFFFFFFFF, (steps0 + j + 1) * L, float(w),
-                          ops._stream())
+                if gs["freed"][k] is not None:
+                    stage.wait_event(gs["freed"][k])            # the pair that last read this slot's staging fields is done
+                with torch.cuda.stream(stage):
+                    slot.seeds[:bs].copy_(loader.batch_seeds(order_of(epoch), g), non_blocking=True)
+                    _lib.call("ngnn_step_ctl_set", ops._ptr(slot.ctl_next), epoch & 0xFFFFFFFF, g & 0xFFFFFFFF, (steps0 + j + 1) * L,
+                              float(w), ops._stream())
+                    ev = torch.cuda.Event()
+                    ev.record()
+                gs["staged"][k] = ev
                 return bs
+
+            def mark_freed(k):
+                ev = torch.cuda.Event()
+                ev.record()
+                gs["freed"][k] = ev
 
             lib = _lib.load()
             log = torch.empty((n_steps, 2), dtype=torch.float32, pin_memory=True) if log_every_step else None
             self.stats.zero_()
             # prologue: the first block is sampled eagerly into slot 0
             bs_cur = stage_block(0, 0)
+            cur.wait_event(gs["staged"][0])
+            gs["slots"][0].ctl.copy_(gs["slots"][0].ctl_next, non_blocking=True)
             loader.launch_sample(gs["slots"][0], None, bs_cur, 0, 0, use_ctl=True, transposes=gs["T"])
+            mark_freed(0)
             for j in range(n_steps):
                 k = j & 1
                 bs_next = stage_block(j + 1, 1 - k) if j + 1 < n_steps else 0
+                if bs_next > 0:
+                    cur.wait_event(gs["staged"][1 - k])
                 self.steps += 1
                 # replay only when this round and the next are full on EVERY rank (all ranks then agree on graph vs eager)
                 i_cur, i_next = (start_step + j) % spe, (start_step + j + 1) % spe
@@ -342,6 +366,8 @@ class Trainer:
                     self.replayed_launches += gs["graph_launches"][k]
                 else:
                     self._enqueue_pair(gs, k, bs_cur, bs_next)
+                if bs_next > 0:
+                    mark_freed(1 - k)                           # this pair's sampler was the reader of slot 1-k's staging fields
                 if log is not None:
                     log[j].copy_(self.stats, non_blocking=True)
                 if on_step is not None:
