@@ -224,6 +224,8 @@ def run_ours(args):
     # outside it, to count their edges (and the distinct table rows their layer-1 aggregation reads)
     scratch = BlockSlot(loader, 0)
 
+    tbytes = []
+
     def region_blocks(first, steps, want_bytes=False):
         edges, nbytes = [], []
         for j in range(first, first + steps):
@@ -236,6 +238,12 @@ def run_ours(args):
             if want_bytes:
                 n_dst, e1 = c[min(L - 1, H)], c[H + 1 + min(L, H)]
                 nbytes.append(agg_l1_bytes(torch.cat([scratch.colg[:e1], scratch.n_id[:n_dst]]), n_dst, e1, sh.features))
+                if L >= 2:
+                    # K-AGG-T into layer 1's output rows: n_src = those rows, n_dst2 = layer 2's destination rows, e2 = its edges
+                    n_src, n_dst2, e2, Fh = n_dst, c[min(L - 2, H)], c[H + 1 + min(L - 1, H)], sh.hidden
+                    survey = 4 * Fh * n_dst2 + 4 * e2 + 4 * (n_src + 1) + 4 * Fh * n_src          # SURVEY §8(d), literal
+                    fused = survey + 4 * Fh * n_src + 4 * Fh * n_dst2                               # + gate rows read + root-gradient rows read
+                    tbytes.append((fused, survey))
         return edges, nbytes
 
     # ---- `value`: every input (graph, features, labels, the epochs' seed orders) resident in HBM ----
@@ -305,8 +313,22 @@ def run_ours(args):
     agg_ms = list(buf[:cnt.value])
     _lib.call("ngnn_probe_read_device_clock", buf, Kp, ctypes.byref(cnt))
     agg_ms_dev = [v for v in buf[:cnt.value] if v > 0]
+    _lib.call("ngnn_probe_read_agg_t", buf, Kp, ctypes.byref(cnt))
+    aggt_ms = list(buf[:cnt.value])
     _lib.call("ngnn_probe_enable", 0)
     _, agg_bytes = region_blocks(start + W, Kp, want_bytes=True)
+    k_agg_t = None
+    if aggt_ms and tbytes:
+        t_us = 1e3 * sum(aggt_ms) / len(aggt_ms)
+        fused, survey = sum(b[0] for b in tbytes) / len(tbytes), sum(b[1] for b in tbytes) / len(tbytes)
+        k_agg_t = {"kernel": "K-AGG-T into layer 1's output rows (transpose-sum of dmean + root-gradient rows, fused ReLU/dropout gate)",
+                   "bound": "hbm", "avg_launch_us": t_us, "achieved": fused / (t_us * 1e-6) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                   "frac": fused / (t_us * 1e-6) / 1e9 / peak_gbs, "algorithmic_bytes_per_launch": fused,
+                   "frac_survey_formula": survey / (t_us * 1e-6) / 1e9 / peak_gbs, "survey_bytes_per_launch": survey,
+                   "note": "same eagerly issued steps and event-pair timing as the K-AGG figure; algorithmic bytes = SURVEY §8(d)'s "
+                           "K-AGG-T formula (dmean rows read, indices, extents, dX rows written) + what the fused epilogue must also "
+                           "read: the gate rows (the saved layer output) and the root-gradient rows; frac_survey_formula uses the "
+                           "literal formula alone"}
     achieved = (sum(agg_bytes) / len(agg_bytes)) / (sum(agg_ms) / len(agg_ms) * 1e-3) / 1e9 if agg_ms else None
     roofline = {"kernel": "K-AGG layer 1 (mean of sampled in-neighbours + root gather from the resident table)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -324,6 +346,7 @@ def run_ours(args):
                 if agg_ms_dev else None,
                 "algorithmic_bytes_per_launch": sum(agg_bytes) / len(agg_bytes) if agg_bytes else None,
                 "share_of_step": (sum(agg_ms) / len(agg_ms)) / (ms_total / K) if agg_ms else None,
+                "k_agg_t": k_agg_t,
                 "timing": f"CUDA events on the launching stream around this kernel's launch in {Kp} eagerly issued steps, queued "
                           f"while a spin kernel holds the GPU so that the host is ahead ({eager_ms / Kp:.3f} ms/step vs "
                           f"{ms_total / K:.3f} replayed); share_of_step is against the replayed step"}

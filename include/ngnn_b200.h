@@ -399,6 +399,9 @@ int32_t ngnn_set_step_overlap(int32_t on);
  * per-launch durations in milliseconds.  ngnn_probe_enable(0) disables and frees the events.                         */
 int32_t ngnn_probe_enable(int32_t max_samples);
 int32_t ngnn_probe_read(float* ms /*(host)[cap]*/, int32_t cap, int32_t* n /*(host)*/);
+/* The same steps' second event pair: around the K-AGG-T launch that writes the gradient of layer 1's output rows (the widest
+ * transpose-sum of the step; networks with one layer have none). */
+int32_t ngnn_probe_read_agg_t(float* ms /*(host)[cap]*/, int32_t cap, int32_t* n /*(host)*/);
 /* The same launches by the device's own clock: last CTA end - first CTA start (%globaltimer), i.e. without the two event
  * records and the launch latency an event pair includes.  Synchronises the device.                               */
 int32_t ngnn_probe_read_device_clock(float* ms /*(host)[cap]*/, int32_t cap, int32_t* n /*(host)*/);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "ngnn_probe_enable": (c_int32, [c_int32]),
     "ngnn_probe_read": (c_int32, [_P, c_int32, _P]),
     "ngnn_probe_read_device_clock": (c_int32, [_P, c_int32, _P]),
+    "ngnn_probe_read_agg_t": (c_int32, [_P, c_int32, _P]),
     "ngnn_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P,
                                  c_int32, _P]),
     "ngnn_sample_capacity": (c_int32, [c_int32, _P, c_int32, c_int64, _P, _P]),

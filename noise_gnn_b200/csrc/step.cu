@@ -127,6 +127,8 @@ static int32_t ensure_aux(AuxCtx** out) {
 // Optional in-situ timing of the layer-1 aggregation launch inside ngnn_sage_step (bench.py's roofline):
 // CUDA events recorded on the caller's stream around that one launch, a pair per step.
 static cudaEvent_t* g_probe_ev = nullptr;
+static cudaEvent_t* g_probe_t_ev = nullptr;           // second pair per sample: the K-AGG-T launch into layer 1's output rows
+static unsigned char* g_probe_t_done = nullptr;
 static int g_probe_cap = 0, g_probe_n = 0;
 static unsigned long long* g_probe_clk = nullptr;     // device [2 * cap]: (min start, max end) %globaltimer of each probed launch
 
@@ -137,13 +139,18 @@ using namespace ngnn;
 extern "C" {
 
 int32_t ngnn_probe_enable(int32_t max_samples) {
-  for (int i = 0; i < 2 * g_probe_cap; ++i) cudaEventDestroy(g_probe_ev[i]);
+  for (int i = 0; i < 2 * g_probe_cap; ++i) { cudaEventDestroy(g_probe_ev[i]); cudaEventDestroy(g_probe_t_ev[i]); }
   delete[] g_probe_ev;
+  delete[] g_probe_t_ev;
+  delete[] g_probe_t_done;
+  g_probe_t_ev = nullptr; g_probe_t_done = nullptr;
   if (g_probe_clk) cudaFree(g_probe_clk);
   g_probe_ev = nullptr; g_probe_clk = nullptr; g_probe_cap = 0; g_probe_n = 0;
   if (max_samples <= 0) return NGNN_OK;
   g_probe_ev = new cudaEvent_t[2 * (size_t)max_samples];
-  for (int i = 0; i < 2 * max_samples; ++i) NGNN_CUDA(cudaEventCreate(&g_probe_ev[i]));
+  g_probe_t_ev = new cudaEvent_t[2 * (size_t)max_samples];
+  g_probe_t_done = new unsigned char[(size_t)max_samples]();
+  for (int i = 0; i < 2 * max_samples; ++i) { NGNN_CUDA(cudaEventCreate(&g_probe_ev[i])); NGNN_CUDA(cudaEventCreate(&g_probe_t_ev[i])); }
   {   // (a measurement facility: the one place the library allocates) start words = all ones, end words = 0
     NGNN_CUDA(cudaMalloc(&g_probe_clk, 2 * (size_t)max_samples * sizeof(unsigned long long)));
     unsigned long long* h = new unsigned long long[2 * (size_t)max_samples];
@@ -162,6 +169,19 @@ int32_t ngnn_probe_read(float* ms, int32_t cap, int32_t* n) {
   for (int i = 0; i < m; ++i) {
     NGNN_CUDA(cudaEventSynchronize(g_probe_ev[2 * i + 1]));
     NGNN_CUDA(cudaEventElapsedTime(&ms[i], g_probe_ev[2 * i], g_probe_ev[2 * i + 1]));
+  }
+  *n = m;
+  return NGNN_OK;
+}
+
+int32_t ngnn_probe_read_agg_t(float* ms, int32_t cap, int32_t* n) {
+  NGNN_REQUIRE(ms && n, NGNN_E_INVALID, "probe_read_agg_t: null pointer");
+  int m = 0;
+  for (int i = 0; i < g_probe_n && m < cap; ++i) {
+    if (!g_probe_t_done || !g_probe_t_done[i]) continue;
+    NGNN_CUDA(cudaEventSynchronize(g_probe_t_ev[2 * i + 1]));
+    NGNN_CUDA(cudaEventElapsedTime(&ms[m], g_probe_t_ev[2 * i], g_probe_t_ev[2 * i + 1]));
+    ++m;
   }
   *n = m;
   return NGNN_OK;
@@ -365,8 +385,17 @@ static int32_t sage_step_body(const ngnn_sage_model_t* model, const float* param
       if (rc != NGNN_OK) return rc;
     }
     // dY of the previous layer = gate(prev output) * (transpose-sum of dmean + droot on the root rows)
+    // (second probe of ngnn_probe_*: the K-AGG-T launch into layer 1's output rows, the widest of the step; the probe index was
+    //  advanced by the layer-1 K-AGG of this step)
+    bool probe_t = i == 1 && g_probe_t_ev != nullptr && g_probe_n >= 1 && g_probe_n <= g_probe_cap && !g_probe_t_done[g_probe_n - 1];
+    if (probe_t) {
+      cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &capturing) != cudaSuccess || capturing != cudaStreamCaptureStatusNone) { cudaGetLastError(); probe_t = false; }
+    }
+    if (probe_t) cudaEventRecord(g_probe_t_ev[2 * (g_probe_n - 1)], st);
     rc = agg_bwd_impl(colptr_t, row_t, F32(pl.dmean), lp.ldf, nodes_ext(lp.b, lp.n_src_max, lp.n_src), lp.F, F32(pl.droot), lp.ldf,
                       n_rows, F32(prev.out), prev.ldo, 1.0f / (1.0f - p_drop), F32(prev.dy), prev.ldo, st);
+    if (probe_t) { cudaEventRecord(g_probe_t_ev[2 * (g_probe_n - 1) + 1], st); g_probe_t_done[g_probe_n - 1] = 1; }
     if (rc != NGNN_OK) return rc;
   }
   return NGNN_OK;
