@@ -74,17 +74,8 @@ if args.sweep:
     _lib.call("ngnn_set_tuning", 2, 32)
     _lib.call("ngnn_set_tuning", 3, 1)
 run("default")
-# rows staged through shared memory by the async copy engines (k_agg_fwd_bulk): mode 1xx = UBLKCP, 2xx = LDGSTS;
-# x0y = 8 neighbours per unit, x1y = 16; y = ring depth
-blk0 = batches[0].block
-n0, e0, _ = SAGE.layer_extents(blk0, sh.layers)[0]
-ref_m, ref_r = ops.agg_fwd(blk0.rowptr, blk0.col_global, loader.x, n0, root_idx=blk0.n_id)
-for v in (104, 106, 113, 114, 204, 206, 213, 214):
-    _lib.call("ngnn_set_tuning", 5, v)
-    m, r = ops.agg_fwd(blk0.rowptr, blk0.col_global, loader.x, n0, root_idx=blk0.n_id)
-    ok = torch.equal(m, ref_m) and torch.equal(r, ref_r)
-    run(f"smem-staged v={v} bitwise_equal={ok}")
-_lib.call("ngnn_set_tuning", 5, 0)
+# (round 1 also timed a variant with the neighbour rows staged through shared memory by the async copy engines — UBLKCP /
+#  LDGSTS, 75-83 us against 50 — which was removed in round 2; profiles/r01_kagg_experiments.txt keeps its numbers)
 
 # ---- K-AGG-T on the layer-2 backward shape of the same blocks: dY_1 = gate(h_1) * (A^T dmean_2 + droot_2)
 F2 = sh.hidden
