@@ -741,6 +741,7 @@ extern "C" int32_t ngnn_set_wgrad_splits(int32_t s);     // gemm.cu
 extern "C" {
 
 int32_t ngnn_set_tuning(int32_t key, int32_t value) {
+  if (key == 16 && (value == 8 || value == 16 || value == 32)) { ngnn::g_draw_group = value; return NGNN_OK; }
   if (key == 0) { g_tune_unroll = value; return NGNN_OK; }
   if (key == 1 && (value == 128 || value == 256 || value == 512)) { g_tune_threads = value; return NGNN_OK; }
   if (key == 2 && (value == 32 || value == 16 || value == 8)) { g_tune_group = value; return NGNN_OK; }

@@ -54,6 +54,7 @@ __device__ __forceinline__ void pdl_trigger() {}
 #endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 extern int g_use_pdl;
+extern int g_draw_group;        // sampler.cu: fewest lanes per frontier node in k_hop_draw (ngnn_set_tuning(16, g))
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -32,6 +32,7 @@ constexpr int kDrawTile = 64;    // frontier nodes per CTA of k_hop_draw: 8 warp
                                  // in flight: 256 nodes per CTA (32 per warp, one after the other) took 79 us on the 76.8 k
                                  // frontier of a products block, one node per warp (round 1) 14 us.
 constexpr int kDrawThreads = 256;
+int g_draw_group = 8;            // ngnn_set_tuning(16, g): fewest lanes per frontier node in k_hop_draw (8 / 16 / 32; 32 = one node per warp pass)
 constexpr int kScanTile = 1024;  // positions per CTA of k_hop_assign / k_tscan (256 threads x 4)
 constexpr int kSortSmem = 4096;  // longest transposed row sorted in shared memory by a CTA
 
@@ -201,7 +202,9 @@ struct DrawArgs {
 // decided in registers (Floyd's subset algorithm run cooperatively: one shuffle + one vote per draw, no memory), then
 // every lane reads ITS neighbour id and relabel slot at once — one round of dependent DRAM latencies per node instead of
 // one per draw.  !WARP: one thread per node, any fan-out.  Same positions, emission order and Philox stream as the C oracle.
-template <bool WARP>
+// WARP = lanes per frontier node (8, 16 or 32: the smallest that holds the fan-out, so a fan-out of 5 runs four nodes per warp
+// pass — the draw is bound by instruction issue, Philox + Floyd per node, not by bytes), or 0 = one thread per node.
+template <int WARP>
 __global__ void __launch_bounds__(kDrawThreads) k_hop_draw(const DrawArgs a) {
   __shared__ int s_v[kDrawTile], s_beg[kDrawTile], s_d[kDrawTile], s_off[kDrawTile];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(kDrawThreads) k_hop_draw(const DrawArgs a) {
   if (tile == (int)gridDim.x - 1 && tid == kDrawThreads - 1) a.counts[H + 2 + h] = e_base + sc.total;   // edges after this hop
   if (tid < kDrawTile && i < fr) a.rowptr[lo + i + 1] = e_base + off + k;
 
-  if (!WARP) {
+  if (WARP == 0) {
     // one thread per node
     if (k == 0) return;
     auto emit = [&](int32_t j, int32_t pos) {
@@ -264,52 +267,55 @@ __global__ void __launch_bounds__(kDrawThreads) k_hop_draw(const DrawArgs a) {
     return;
   }
 
-  // one warp per node of the tile, 8 nodes per warp.  The positions of all 8 nodes are decided first (registers only), then
-  // the 8 neighbour-id loads go out together, then the 8 relabel-map loads: two rounds of DRAM latency per warp instead of
-  // two per node.
+  // G lanes per node, 8 nodes per warp in NP passes of 32 / G nodes.  The positions of all the warp's nodes are decided first
+  // (registers only), then their neighbour-id loads go out together, then the relabel-map loads: two rounds of DRAM latency
+  // per warp instead of two per node.
   if (tid < kDrawTile) { s_v[tid] = v; s_beg[tid] = beg; s_d[tid] = d; s_off[tid] = off; }
   __syncthreads();
-  const unsigned full = 0xffffffffu;
+  constexpr int G = WARP > 0 ? WARP : 32;
   constexpr int NPW = kDrawTile / (kDrawThreads / 32);       // nodes per warp
-  int32_t pos[NPW], g[NPW];
+  constexpr int NP = NPW * G / 32;                           // passes
+  const int gl = lane & (G - 1), sg = lane / G;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (sg * G));
+  int32_t pos[NP], g[NP];
 #pragma unroll
-  for (int u = 0; u < NPW; ++u) {
-    const int jn = warp + u * (kDrawThreads / 32);
+  for (int u = 0; u < NP; ++u) {
+    const int jn = warp + (u * (32 / G) + sg) * (kDrawThreads / 32);
     const int32_t nv = s_v[jn], nd = s_d[jn];
     const int32_t nk = nv < 0 ? 0 : (replace ? (nd > 0 ? fanout : 0) : min(nd, fanout));
-    int32_t p = lane;                                          // take all, stored order
-    if (nk > 0 && (replace || nd > fanout)) {                  // warp-uniform
-      const Philox4 r = philox4x32_10((uint32_t)nv, ((uint32_t)h << 16) | (uint32_t)(lane >> 2), batch_idx, epoch, a.seed_lo, a.seed_hi);
-      const uint32_t w = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
+    int32_t p = gl;                                            // take all, stored order
+    if (nk > 0 && (replace || nd > fanout)) {                  // uniform within the node's lane group
+      const Philox4 r = philox4x32_10((uint32_t)nv, ((uint32_t)h << 16) | (uint32_t)(gl >> 2), batch_idx, epoch, a.seed_lo, a.seed_hi);
+      const uint32_t w = (gl & 3) == 0 ? r.x : (gl & 3) == 1 ? r.y : (gl & 3) == 2 ? r.z : r.w;
       if (replace) {
         p = (int32_t)mulhi32(w, (uint32_t)nd);
       } else {
         // Robert Floyd: for jj = d-k .. d-1: t = U[0,jj]; take t unless already taken, else take jj
         int32_t mine = -1;
         for (int32_t j = 0; j < nk; ++j) {
-          const uint32_t wj = __shfl_sync(full, w, j);
+          const uint32_t wj = __shfl_sync(gmask, w, j, G);
           const int32_t jj = nd - nk + j;
           int32_t t = (int32_t)mulhi32(wj, (uint32_t)(jj + 1));
-          if (__any_sync(full, lane < j && mine == t)) t = jj;
-          if (lane == j) mine = t;
+          if (__any_sync(gmask, gl < j && mine == t)) t = jj;
+          if (gl == j) mine = t;
         }
         p = mine;
       }
     }
-    pos[u] = lane < nk ? p : -1;
+    pos[u] = gl < nk ? p : -1;
   }
 #pragma unroll
-  for (int u = 0; u < NPW; ++u) {
-    const int jn = warp + u * (kDrawThreads / 32);
+  for (int u = 0; u < NP; ++u) {
+    const int jn = warp + (u * (32 / G) + sg) * (kDrawThreads / 32);
     g[u] = pos[u] >= 0 ? __ldg(a.row + s_beg[jn] + pos[u]) : -1;
   }
-  int32_t lof[NPW];
+  int32_t lof[NP];
 #pragma unroll
-  for (int u = 0; u < NPW; ++u) {
-    const int jn = warp + u * (kDrawThreads / 32);
+  for (int u = 0; u < NP; ++u) {
+    const int jn = warp + (u * (32 / G) + sg) * (kDrawThreads / 32);
     lof[u] = 0;
     if (g[u] >= 0) {
-      const int32_t p = e_base + s_off[jn] + lane;
+      const int32_t p = e_base + s_off[jn] + gl;
       a.col_global[p] = g[u];
       if (a.edge_dst) a.edge_dst[p] = lo + tile * kDrawTile + jn;
       if (a.e_pos) a.e_pos[p] = s_beg[jn] + pos[u];
@@ -317,9 +323,9 @@ __global__ void __launch_bounds__(kDrawThreads) k_hop_draw(const DrawArgs a) {
     }
   }
 #pragma unroll
-  for (int u = 0; u < NPW; ++u) {
-    const int jn = warp + u * (kDrawThreads / 32);
-    if (g[u] >= 0 && lof[u] < 0) atomicMin(a.first_pos + g[u], s_off[jn] + lane);
+  for (int u = 0; u < NP; ++u) {
+    const int jn = warp + (u * (32 / G) + sg) * (kDrawThreads / 32);
+    if (g[u] >= 0 && lof[u] < 0) atomicMin(a.first_pos + g[u], s_off[jn] + gl);
   }
 }
 
@@ -333,16 +339,20 @@ __global__ void __launch_bounds__(256) k_hop_assign(const int32_t* __restrict__ 
   const int32_t n_prev = counts[h];
   const int32_t e_base = counts[H + 1 + h], e_h = counts[H + 2 + h] - e_base;
   const int64_t p0 = (int64_t)tile * kScanTile + tid * 4;
-  int32_t g[4];
+  // the two map reads of a position are random DRAM accesses: all eight of a thread are issued before any is looked at
+  int32_t g[4], lof[4], fp[4];
   int f = 0;
 #pragma unroll
+  for (int q = 0; q < 4; ++q) g[q] = (p0 + q < e_h) ? __ldg(col_global + e_base + p0 + q) : -1;
+#pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int64_t p = p0 + q;
-    g[q] = -1;
-    if (p < e_h) {
-      const int32_t gg = col_global[e_base + p];
-      if (local_of[gg] < 0 && first_pos[gg] == (int32_t)p) { g[q] = gg; ++f; }
-    }
+    lof[q] = g[q] >= 0 ? local_of[g[q]] : 0;
+    fp[q] = g[q] >= 0 ? __ldg(first_pos + g[q]) : -1;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (g[q] >= 0 && lof[q] < 0 && fp[q] == (int32_t)(p0 + q)) ++f;
+    else g[q] = -1;
   }
   const TileScan sc = tile_scan_256(f, tile, state);
   int32_t lid = n_prev + sc.excl;
@@ -618,8 +628,10 @@ int32_t ngnn_sample_block_ex(const int32_t* colptr, const int32_t* row, int64_t 
     a.rowptr = rowptr; a.col_global = col_global; a.e_pos = e_pos; a.edge_dst = edge_dst;
     a.local_of = w.local_of; a.first_pos = w.first_pos; a.state = w.st_draw[h]; a.ticket = w.tickets + 2 * h;
     const unsigned gd = (unsigned)draw_tiles(c.fr_max[h]);
-    if (fanouts[h] <= 32) k_hop_draw<true><<<gd, kDrawThreads, 0, st>>>(a);
-    else k_hop_draw<false><<<gd, kDrawThreads, 0, st>>>(a);
+    if (fanouts[h] <= 8 && g_draw_group <= 8) k_hop_draw<8><<<gd, kDrawThreads, 0, st>>>(a);
+    else if (fanouts[h] <= 16 && g_draw_group <= 16) k_hop_draw<16><<<gd, kDrawThreads, 0, st>>>(a);
+    else if (fanouts[h] <= 32) k_hop_draw<32><<<gd, kDrawThreads, 0, st>>>(a);
+    else k_hop_draw<0><<<gd, kDrawThreads, 0, st>>>(a);
     NGNN_LAUNCH_CHECK();
     k_hop_assign<<<(unsigned)scan_tiles(c.e_max[h]), 256, 0, st>>>(col_global, counts, h, H, w.local_of, w.first_pos, n_id,
                                                                  w.st_assign[h], w.tickets + 2 * h + 1);
