@@ -1201,9 +1201,10 @@ struct TcWgradPlan {
 static int g_tc_wgrad_splits = 0;   // ngnn_set_tuning(8, s): force the number of reduction slices (0 = automatic)
 static inline TcWgradPlan tc_wgrad_plan(int64_t n, int64_t F, int64_t O, int num_segs) {
   TcWgradPlan pl;
-  pl.BN = F >= TW_BN_MAX ? TW_BN_MAX : round_up_i(F, 16);
+  // equal N tiles: F = 200 (products layer 1, [mean | root] side by side) is 2 x 112 columns, not 128 + 72 padded to 128
+  pl.tiles_per_seg = (int32_t)ceil_div(F, (int64_t)TW_BN_MAX);
+  pl.BN = round_up_i(ceil_div(F, (int64_t)pl.tiles_per_seg), 16);
   pl.nbox = (pl.BN + 31) / 32;
-  pl.tiles_per_seg = (int32_t)ceil_div(F, pl.BN);
   pl.ts = g_tc_ts != 0;
   const uint32_t stage = (pl.ts ? 1u : 2u) * 4u * TW_BOX_BYTES + 2u * (uint32_t)pl.nbox * TW_BOX_BYTES;
   int st = (int)((TC_SMEM_LIMIT - 2048u) / stage);
