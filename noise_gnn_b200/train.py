@@ -277,10 +277,11 @@ class Trainer:
 
         Every step is the SAME launch sequence over fixed buffers — sample the next block (side stream) while the current
         one runs forward / loss / backward / [all-reduce] / Adam — with all block extents left on the device, so it is
-        captured once per buffer parity in a CUDA graph and replayed: per step the host issues the next block's seed ids
-        (H2D from pinned memory, or a device copy when ``seeds_resident``), one control-word kernel, one graph launch and,
-        with ``log_every_step``, an asynchronous read-back of the loss / accuracy accumulators (the reference reads them
-        every step, src/pipeline.py:164-165).  The first two steps and ragged batches run the same calls eagerly.
+        captured once per buffer parity in a CUDA graph and replayed: per step the host issues, on a staging stream and one
+        step ahead, the next block's seed ids (H2D from pinned memory, or a device copy when ``seeds_resident``) and one
+        control-word kernel, then one graph launch and, with ``log_every_step``, an asynchronous read-back of the loss /
+        accuracy accumulators (the reference reads them every step, src/pipeline.py:164-165).  The first two steps and
+        ragged batches run the same calls eagerly.
         ``on_step(j)`` is called after step j has been enqueued.
 
         Returns (sum of step losses, correct seed predictions, per-step cumulative (loss, correct) snapshots or None)."""
